@@ -1,0 +1,125 @@
+/*
+ * b200_hotpath.h -- C ABI of the B200-native training-step hot path.
+ *
+ * The reference (arthurcolle/mlx-cuda-distributed-pretraining) has no native code and no FFI: its
+ * hot path is Python over mlx.core ops.  This header is therefore the boundary a maintainer would
+ * bind *instead of* those mlx.core call sites; each entry point cites the reference lines whose
+ * arithmetic it replaces.  All functions:
+ *   - take raw device pointers + explicit sizes/strides + a cudaStream_t (passed as void*),
+ *   - never allocate: scratch comes from the caller via *_workspace_bytes() queries,
+ *   - return 0 on success, a negative b200 error code otherwise (message: b200_last_error()),
+ *   - are asynchronous on `stream` and re-entrant across streams.
+ * Element types: "bf16" = __nv_bfloat16, "f32" = float.  Matrices are row-major.
+ */
+#ifndef B200_HOTPATH_H_
+#define B200_HOTPATH_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_OK 0
+#define B200_ERR_ARG (-1)
+#define B200_ERR_CUDA (-2)
+#define B200_ERR_DEVICE (-3)
+#define B200_ERR_WORKSPACE (-4)
+
+/* ---- library / device ---------------------------------------------------------------------- */
+int b200_version(void);                 /* ABI version (monotonic integer) */
+const char* b200_last_error(void);      /* thread-local message of the last failing call */
+int b200_device_ok(void);               /* 1 if the current device is compute capability 10.x */
+
+/* ---- dense contraction engine (tcgen05 + TMA) ----------------------------------------------
+ * D[b] = alpha*alpha_vec[b] * op(A[b]) op(B[b]) + beta*beta_vec[b] * C[b],  b in [0,batch)
+ * replaces: `@` / mx.matmul in optimizers/muon.py:76-78, optimizers/shampoo.py:121,250,254,287-290
+ * a_mn=0: A is [M,K] row-major (K-major);  a_mn=1: A is stored [K,M] row-major (MN-major)
+ * b_mn=0: B is [N,K] row-major (K-major);  b_mn=1: B is stored [K,N] row-major (MN-major)
+ * A,B bf16; C,D bf16 (out_f32=0) or f32 (out_f32=1); accumulate fp32 in TMEM.
+ * alpha_vec/beta_vec: optional per-batch device scalars (NULL = 1).  force_bn: 0 auto | 128 | 256.
+ */
+int b200_gemm_bf16(int a_mn, int b_mn, int M, int N, int K, int batch,
+                   const void* A, long long lda, long long strideA,
+                   const void* B, long long ldb, long long strideB,
+                   const void* C, long long ldc, long long strideC,
+                   void* D, long long ldd, long long strideD,
+                   int out_f32, float alpha, float beta,
+                   const float* alpha_vec, const float* beta_vec, int force_bn, void* stream);
+
+/* ---- Muon (optimizers/muon.py) ---------------------------------------------------------------
+ * b200_newton_schulz: Muon.zeropower_via_newtonschulz5 (muon.py:54-83) on a batch of same-shape
+ * matrices.  x_in: bf16 [batch,rows,cols], *un-normalised*; inv_norm[b] = 1/(||x_b||_F+eps) and
+ * inv_norm_sq[b] = inv_norm[b]^2 (from b200_muon_momentum + b200_ns_scales) fold muon.py:72-73
+ * into the first iteration.  x_out: bf16 [batch,rows,cols], must not alias x_in.
+ */
+size_t b200_newton_schulz_workspace_bytes(int batch, int rows, int cols, int steps);
+int b200_newton_schulz(const void* x_in, void* x_out, int batch, int rows, int cols, int steps,
+                       float a, float b, float c, const float* inv_norm, const float* inv_norm_sq,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* muon.py:101,105: buf = (1-mu)*g*gscale + mu*buf ; u = nesterov ? g*gscale + mu*buf : buf.
+ * g: [batch,numel] bf16 (g_is_bf16=1) or f32; buf f32; u bf16; sumsq[b] = sum(u_b^2) (zeroed
+ * inside). */
+int b200_muon_momentum(const void* g, int g_is_bf16, float* buf, void* u_bf16, float* sumsq,
+                       long long numel, int batch, float mu, int nesterov, float gscale,
+                       void* stream);
+/* muon.py:72-73: inv_norm = 1/(sqrt(sumsq)+eps), inv_norm_sq = inv_norm^2 */
+int b200_ns_scales(const float* sumsq, float* inv_norm, float* inv_norm_sq, int batch, float eps,
+                   void* stream);
+/* muon.py:111-114 (and the in-place apply the reference forgot):
+ * p32 += s*x ; p16 = bf16(p32) if p16 != NULL.  x bf16 (x_is_bf16=1) or f32. */
+int b200_axpy_update(float* p32, void* p16, const void* x, int x_is_bf16, long long n, float s,
+                     void* stream);
+/* muon.py:123-138 non-2-D fallback: momentum as above, p -= lr*u */
+int b200_sgd_momentum(float* p32, void* p16, const void* g, int g_is_bf16, float* buf,
+                      long long n, float mu, int nesterov, float lr, float gscale, void* stream);
+
+/* ---- AdamW (core/training.py:821 -> mlx.optimizers.AdamW; enhanced_optimizers.py:157-184) ----
+ * p *= 1-lr*wd ; m = b1 m + (1-b1) g ; v = b2 v + (1-b2) g^2 ;
+ * p -= (lr/bc1) * m / (sqrt(v)/sqrt(bc2) + eps)        (bc1=bc2=1: no bias correction) */
+int b200_adamw(float* p32, void* p16, const void* g, int g_is_bf16, float* m, float* v,
+               long long n, float lr, float b1, float b2, float eps, float wd, float bc1,
+               float bc2, float gscale, void* stream);
+/* Adam step direction without applying it (Shampoo grafting, optimizers/shampoo.py:162-167,326) */
+int b200_adam_direction(float* d, const void* g, int g_is_bf16, float* m, float* v, long long n,
+                        float lr, float b1, float b2, float eps, float bc1, float bc2,
+                        float gscale, void* stream);
+
+/* ---- gradient post-processing (core/training.py:1664-1666,1671-1680) --------------------------
+ * acc = (init?0:acc) + clamp(g,-clip,clip)*scale ; clip<=0 disables the clamp */
+int b200_clip_accum(const void* g, int g_is_bf16, float* acc, long long n, float clip,
+                    float scale, int init, void* stream);
+/* out[b] (+)= sum(x[b,:]^2)   (optimizers/shampoo.py:300-301 Frobenius norms) */
+int b200_sumsq(const void* x, int x_is_bf16, float* out, long long numel, int batch,
+               int zero_first, void* stream);
+/* hi = bf16((src + diag_add*I)*scale), lo = bf16(that - hi) (lo may be NULL); strided [rows,cols] */
+int b200_split_bf16(const float* src, long long ld_src, void* hi, void* lo, long long ld_dst,
+                    int rows, int cols, float scale, float diag_add, void* stream);
+
+/* ---- RMSNorm (arch/llama.py:50-56) and RoPE (arch/llama_standard.py:74-75,117-127) ------------ */
+int b200_rmsnorm_fwd(const void* x, const void* w, void* y, float* rstd, int rows, int H,
+                     float eps, int is_bf16, void* stream);
+int b200_rmsnorm_bwd(const void* dy, const void* x, const void* w, const float* rstd, void* dx,
+                     float* dw_f32, int rows, int H, int is_bf16, void* stream);
+/* x,y: [B,S,NH,D]; cos_t,sin_t: f32 [S,D/2]; backward=1 applies the inverse rotation */
+int b200_rope(const void* x, void* y, const float* cos_t, const float* sin_t, int B, int S, int NH,
+              int D, int backward, int is_bf16, void* stream);
+
+/* ---- fused causal / GQA attention (arch/flash_attention.py:97-156 + its autograd) --------------
+ * q: bf16 [B,S,H,D], k,v: bf16 [B,S,Hk,D] (q head h uses kv head h/(H/Hk), flash_attention.py:102-120)
+ * o: bf16 [B,S,H,D]; lse: f32 [B,H,S] (natural-log sum-exp of scaled, masked scores)
+ * causal=1 reproduces the additive -inf strictly-upper mask of arch/llama.py:384-387. */
+int b200_attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int B, int S,
+                  int H, int Hk, int D, float scale, int causal, void* stream);
+size_t b200_attn_bwd_workspace_bytes(int B, int S, int H, int Hk, int D);
+int b200_attn_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o,
+                  const float* lse, void* dq, void* dk, void* dv, int B, int S, int H, int Hk,
+                  int D, float scale, int causal, void* workspace, size_t workspace_bytes,
+                  void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200_HOTPATH_H_ */

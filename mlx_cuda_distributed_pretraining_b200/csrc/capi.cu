@@ -1,0 +1,153 @@
+// extern "C" surface of libb200hotpath.so -- see include/b200_hotpath.h for the contract.
+#include "../../include/b200_hotpath.h"
+
+#include "host.h"
+
+namespace b200 {
+int gemm_bf16(bool a_mn, bool b_mn, int M, int N, int K, int batch, const void* A, long long lda,
+              long long strideA, const void* B, long long ldb, long long strideB, const void* C,
+              long long ldc, long long strideC, void* D, long long ldd, long long strideD,
+              bool out_f32, float alpha, float beta, const float* alpha_vec, const float* beta_vec,
+              int force_bn, cudaStream_t stream);
+size_t newton_schulz_workspace_bytes(int batch, int rows, int cols, int steps);
+int newton_schulz(const void* x_in, void* x_out, int batch, int rows, int cols, int steps, float a,
+                  float b, float c, const float* inv_norm, const float* inv_norm_sq, void* ws,
+                  size_t ws_bytes, cudaStream_t stream);
+int muon_momentum(const void* g, int g_is_bf16, float* buf, void* u_bf16, float* sumsq,
+                  long long numel, int batch, float mu, int nesterov, float gscale,
+                  cudaStream_t stream);
+int ns_scales(const float* sumsq, float* inv_norm, float* inv_norm_sq, int batch, float eps,
+              cudaStream_t stream);
+int axpy_update(float* p32, void* p16, const void* x, int x_is_bf16, long long n, float s,
+                cudaStream_t stream);
+int sgd_momentum(float* p32, void* p16, const void* g, int g_is_bf16, float* buf, long long n,
+                 float mu, int nesterov, float lr, float gscale, cudaStream_t stream);
+int adamw(float* p32, void* p16, const void* g, int g_is_bf16, float* m, float* v, long long n,
+          float lr, float b1, float b2, float eps, float wd, float bc1, float bc2, float gscale,
+          cudaStream_t stream);
+int adam_direction(float* d, const void* g, int g_is_bf16, float* m, float* v, long long n,
+                   float lr, float b1, float b2, float eps, float bc1, float bc2, float gscale,
+                   cudaStream_t stream);
+int clip_accum(const void* g, int g_is_bf16, float* acc, long long n, float clip, float scale,
+               int init, cudaStream_t stream);
+int sumsq(const void* x, int x_is_bf16, float* out, long long numel, int batch, int zero_first,
+          cudaStream_t stream);
+int split_bf16(const float* src, long long ld_src, void* hi, void* lo, long long ld_dst, int rows,
+               int cols, float scale, float diag_add, cudaStream_t stream);
+int rmsnorm_fwd(const void* x, const void* w, void* y, float* rstd, int rows, int H, float eps,
+                int is_bf16, cudaStream_t stream);
+int rmsnorm_bwd(const void* dy, const void* x, const void* w, const float* rstd, void* dx,
+                float* dw, int rows, int H, int is_bf16, cudaStream_t stream);
+int rope(const void* x, void* y, const float* cos_t, const float* sin_t, int B, int S, int NH,
+         int D, int backward, int is_bf16, cudaStream_t stream);
+int attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int B, int S, int H,
+             int Hk, int D, float scale, int causal, cudaStream_t stream);
+size_t attn_bwd_workspace_bytes(int B, int S, int H, int Hk, int D);
+int attn_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o,
+             const float* lse, void* dq, void* dk, void* dv, int B, int S, int H, int Hk, int D,
+             float scale, int causal, void* ws, size_t ws_bytes, cudaStream_t stream);
+}  // namespace b200
+
+#define S_(x) reinterpret_cast<cudaStream_t>(x)
+
+extern "C" {
+
+int b200_version(void) { return 1; }
+const char* b200_last_error(void) { return b200::last_error(); }
+
+int b200_device_ok(void) {
+  int dev = 0, major = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return 0;
+  return major == 10 ? 1 : 0;
+}
+
+int b200_gemm_bf16(int a_mn, int b_mn, int M, int N, int K, int batch, const void* A,
+                   long long lda, long long strideA, const void* B, long long ldb,
+                   long long strideB, const void* C, long long ldc, long long strideC, void* D,
+                   long long ldd, long long strideD, int out_f32, float alpha, float beta,
+                   const float* alpha_vec, const float* beta_vec, int force_bn, void* stream) {
+  return b200::gemm_bf16(a_mn != 0, b_mn != 0, M, N, K, batch, A, lda, strideA, B, ldb, strideB, C,
+                         ldc, strideC, D, ldd, strideD, out_f32 != 0, alpha, beta, alpha_vec,
+                         beta_vec, force_bn, S_(stream));
+}
+
+size_t b200_newton_schulz_workspace_bytes(int batch, int rows, int cols, int steps) {
+  return b200::newton_schulz_workspace_bytes(batch, rows, cols, steps);
+}
+int b200_newton_schulz(const void* x_in, void* x_out, int batch, int rows, int cols, int steps,
+                       float a, float b, float c, const float* inv_norm, const float* inv_norm_sq,
+                       void* workspace, size_t workspace_bytes, void* stream) {
+  return b200::newton_schulz(x_in, x_out, batch, rows, cols, steps, a, b, c, inv_norm, inv_norm_sq,
+                             workspace, workspace_bytes, S_(stream));
+}
+int b200_muon_momentum(const void* g, int g_is_bf16, float* buf, void* u_bf16, float* sumsq,
+                       long long numel, int batch, float mu, int nesterov, float gscale,
+                       void* stream) {
+  return b200::muon_momentum(g, g_is_bf16, buf, u_bf16, sumsq, numel, batch, mu, nesterov, gscale,
+                             S_(stream));
+}
+int b200_ns_scales(const float* sumsq, float* inv_norm, float* inv_norm_sq, int batch, float eps,
+                   void* stream) {
+  return b200::ns_scales(sumsq, inv_norm, inv_norm_sq, batch, eps, S_(stream));
+}
+int b200_axpy_update(float* p32, void* p16, const void* x, int x_is_bf16, long long n, float s,
+                     void* stream) {
+  return b200::axpy_update(p32, p16, x, x_is_bf16, n, s, S_(stream));
+}
+int b200_sgd_momentum(float* p32, void* p16, const void* g, int g_is_bf16, float* buf,
+                      long long n, float mu, int nesterov, float lr, float gscale, void* stream) {
+  return b200::sgd_momentum(p32, p16, g, g_is_bf16, buf, n, mu, nesterov, lr, gscale, S_(stream));
+}
+int b200_adamw(float* p32, void* p16, const void* g, int g_is_bf16, float* m, float* v,
+               long long n, float lr, float b1, float b2, float eps, float wd, float bc1,
+               float bc2, float gscale, void* stream) {
+  return b200::adamw(p32, p16, g, g_is_bf16, m, v, n, lr, b1, b2, eps, wd, bc1, bc2, gscale,
+                     S_(stream));
+}
+int b200_adam_direction(float* d, const void* g, int g_is_bf16, float* m, float* v, long long n,
+                        float lr, float b1, float b2, float eps, float bc1, float bc2,
+                        float gscale, void* stream) {
+  return b200::adam_direction(d, g, g_is_bf16, m, v, n, lr, b1, b2, eps, bc1, bc2, gscale,
+                              S_(stream));
+}
+int b200_clip_accum(const void* g, int g_is_bf16, float* acc, long long n, float clip,
+                    float scale, int init, void* stream) {
+  return b200::clip_accum(g, g_is_bf16, acc, n, clip, scale, init, S_(stream));
+}
+int b200_sumsq(const void* x, int x_is_bf16, float* out, long long numel, int batch,
+               int zero_first, void* stream) {
+  return b200::sumsq(x, x_is_bf16, out, numel, batch, zero_first, S_(stream));
+}
+int b200_split_bf16(const float* src, long long ld_src, void* hi, void* lo, long long ld_dst,
+                    int rows, int cols, float scale, float diag_add, void* stream) {
+  return b200::split_bf16(src, ld_src, hi, lo, ld_dst, rows, cols, scale, diag_add, S_(stream));
+}
+int b200_rmsnorm_fwd(const void* x, const void* w, void* y, float* rstd, int rows, int H,
+                     float eps, int is_bf16, void* stream) {
+  return b200::rmsnorm_fwd(x, w, y, rstd, rows, H, eps, is_bf16, S_(stream));
+}
+int b200_rmsnorm_bwd(const void* dy, const void* x, const void* w, const float* rstd, void* dx,
+                     float* dw_f32, int rows, int H, int is_bf16, void* stream) {
+  return b200::rmsnorm_bwd(dy, x, w, rstd, dx, dw_f32, rows, H, is_bf16, S_(stream));
+}
+int b200_rope(const void* x, void* y, const float* cos_t, const float* sin_t, int B, int S, int NH,
+              int D, int backward, int is_bf16, void* stream) {
+  return b200::rope(x, y, cos_t, sin_t, B, S, NH, D, backward, is_bf16, S_(stream));
+}
+int b200_attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int B, int S,
+                  int H, int Hk, int D, float scale, int causal, void* stream) {
+  return b200::attn_fwd(q, k, v, o, lse, B, S, H, Hk, D, scale, causal, S_(stream));
+}
+size_t b200_attn_bwd_workspace_bytes(int B, int S, int H, int Hk, int D) {
+  return b200::attn_bwd_workspace_bytes(B, S, H, Hk, D);
+}
+int b200_attn_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o,
+                  const float* lse, void* dq, void* dk, void* dv, int B, int S, int H, int Hk,
+                  int D, float scale, int causal, void* workspace, size_t workspace_bytes,
+                  void* stream) {
+  return b200::attn_bwd(q, k, v, o, d_o, lse, dq, dk, dv, B, S, H, Hk, D, scale, causal, workspace,
+                        workspace_bytes, S_(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,374 @@
+// Batched bf16 GEMM on tcgen05 tensor cores (sm_100a) with a fused affine epilogue:
+//
+//     D[b] = (alpha * alpha_vec[b]) * op(A[b]) * op(B[b]) + (beta * beta_vec[b]) * C[b]
+//
+// This is the single dense-contraction engine behind Newton-Schulz (optimizers/muon.py:72-78 of
+// the reference: A = X X^T, B = bA + cAA, X = aX + BX) and the Shampoo Kronecker-factor products
+// (optimizers/shampoo.py:116-121, 250-255, 287-290).  Operand layouts are chosen so that no
+// transposed copy of X is ever materialised:
+//     A operand: K-major  (row-major [M, K])  or MN-major (row-major [K, M])
+//     B operand: K-major  (row-major [N, K])  or MN-major (row-major [K, N])
+//
+// Structure: persistent CTAs (one per SM), warp-specialised:
+//     warp 0      TMA producer (one lane) -> STAGES-deep smem ring, 128B swizzle
+//     warp 1      tcgen05.mma issuer (one lane), fp32 accumulators in TMEM, double-buffered
+//     warp 2      TMEM allocator
+//     warps 4-7   epilogue: tcgen05.ld -> registers -> fused alpha/beta/C -> 16-byte stores
+// Tile 128 x BN x 64 with BN in {128, 256}; UMMA 128 x BN x 16.
+#include "common.cuh"
+#include "host.h"
+
+namespace b200 {
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int UMMA_K = 16;
+constexpr int STAGES_BN256 = 4;
+constexpr int STAGES_BN128 = 6;
+constexpr int GEMM_THREADS = 256;
+constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
+
+struct GemmArgs {
+  int M, N, K, batch;
+  int tiles_m, tiles_n;
+  float alpha, beta;
+  const float* alpha_vec;
+  const float* beta_vec;
+  const void* C;
+  long long ldc, strideC;
+  void* D;
+  long long ldd, strideD;
+};
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int STAGES = (BN == 256) ? STAGES_BN256 : STAGES_BN128;
+  static constexpr int B_STAGE_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr int TMEM_COLS = 2 * BN;  // double-buffered accumulator (256 or 512 columns)
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <typename OutT>
+struct OutVec;
+template <>
+struct OutVec<__nv_bfloat16> {
+  static constexpr int N = 8;  // elements per 16-byte access
+};
+template <>
+struct OutVec<float> {
+  static constexpr int N = 4;
+};
+
+template <bool A_MN, bool B_MN, typename OutT, int BN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+                    const __grid_constant__ CUtensorMap tmB, const GemmArgs p) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
+  // barrier layout (8 B each): full[STAGES] | empty[STAGES] | tmem_full[2] | tmem_empty[2] | slot
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+  auto smem_a = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES; };
+  auto smem_b = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES + A_STAGE_BYTES; };
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 4);  // one arrival per epilogue warp
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  const int tiles_per_batch = p.tiles_m * p.tiles_n;
+  const int total_tiles = tiles_per_batch * p.batch;
+  const int num_kb = (p.K + BK - 1) / BK;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ------------------------------- TMA producer -------------------------------------
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int b = tile / tiles_per_batch;
+        const int r = tile - b * tiles_per_batch;
+        const int m0 = (r / p.tiles_n) * BM;
+        const int n0 = (r % p.tiles_n) * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
+          const int k0 = kb * BK;
+          if constexpr (!A_MN) {
+            tma_load_3d(smem_a(stage), &tmA, full_bar(stage), k0, m0, b);
+          } else {
+#pragma unroll
+            for (int i = 0; i < BM / 64; ++i)
+              tma_load_3d(smem_a(stage) + i * 8192, &tmA, full_bar(stage), m0 + i * 64, k0, b);
+          }
+          if constexpr (!B_MN) {
+            tma_load_3d(smem_b(stage), &tmB, full_bar(stage), k0, n0, b);
+          } else {
+#pragma unroll
+            for (int i = 0; i < BN / 64; ++i)
+              tma_load_3d(smem_b(stage) + i * 8192, &tmB, full_bar(stage), n0 + i * 64, k0, b);
+          }
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ------------------------------- MMA issuer ---------------------------------------
+      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MN, B_MN);
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t iter = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
+        const uint32_t acc = iter & 1u;
+        const uint32_t acc_phase = (iter >> 1) & 1u;
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tc_fence_after_sync();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after_sync();
+          const uint32_t a_addr = smem_a(stage);
+          const uint32_t b_addr = smem_b(stage);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // K-major: advance 16 elements = 32 B inside the 128 B swizzle row.
+            // MN-major: advance 16 k-rows = 2 swizzle atoms of 1024 B.
+            const uint64_t da = A_MN ? make_smem_desc_sw128(a_addr + k * 2048, 8192, 1024)
+                                     : make_smem_desc_sw128(a_addr + k * 32, 0, 1024);
+            const uint64_t db = B_MN ? make_smem_desc_sw128(b_addr + k * 2048, 8192, 1024)
+                                     : make_smem_desc_sw128(b_addr + k * 32, 0, 1024);
+            umma_bf16_ss(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(empty_bar(stage));  // frees the smem slot once these MMAs retire
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        umma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+      }
+    }
+  } else if (warp >= 4) {
+    // --------------------------------- epilogue -------------------------------------------
+    constexpr int VEC = OutVec<OutT>::N;
+    const int q = warp - 4;  // TMEM lane quarter == warp_id % 4
+    const int row = q * 32 + lane;
+    uint32_t iter = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
+      const int b = tile / tiles_per_batch;
+      const int r = tile - b * tiles_per_batch;
+      const int m0 = (r / p.tiles_n) * BM;
+      const int n0 = (r % p.tiles_n) * BN;
+      const uint32_t acc = iter & 1u;
+      const uint32_t acc_phase = (iter >> 1) & 1u;
+      const float alpha = p.alpha * (p.alpha_vec ? p.alpha_vec[b] : 1.0f);
+      const float beta = p.beta * (p.beta_vec ? p.beta_vec[b] : 1.0f);
+      const int gm = m0 + row;
+      const bool row_ok = gm < p.M;
+      OutT* drow = reinterpret_cast<OutT*>(p.D) + (long long)b * p.strideD + (long long)gm * p.ldd;
+      const OutT* crow =
+          p.C ? reinterpret_cast<const OutT*>(p.C) + (long long)b * p.strideC + (long long)gm * p.ldc
+              : nullptr;
+
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after_sync();
+      const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + acc * BN;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(t_row + c0, v);
+        tmem_ld_wait();
+        if (row_ok) {
+#pragma unroll
+          for (int g = 0; g < 32; g += VEC) {
+            const int gn = n0 + c0 + g;
+            if (gn < p.N) {
+              float f[VEC];
+#pragma unroll
+              for (int i = 0; i < VEC; ++i) f[i] = alpha * __uint_as_float(v[g + i]);
+              if constexpr (VEC == 8) {
+                if (crow) {
+                  const uint4 cv = ldg128(crow + gn);
+                  const float2 c01 = unpack_bf16x2(cv.x), c23 = unpack_bf16x2(cv.y),
+                               c45 = unpack_bf16x2(cv.z), c67 = unpack_bf16x2(cv.w);
+                  f[0] = fmaf(beta, c01.x, f[0]);
+                  f[1] = fmaf(beta, c01.y, f[1]);
+                  f[2] = fmaf(beta, c23.x, f[2]);
+                  f[3] = fmaf(beta, c23.y, f[3]);
+                  f[4] = fmaf(beta, c45.x, f[4]);
+                  f[5] = fmaf(beta, c45.y, f[5]);
+                  f[6] = fmaf(beta, c67.x, f[6]);
+                  f[7] = fmaf(beta, c67.y, f[7]);
+                }
+                uint4 o;
+                o.x = pack_bf16x2(f[0], f[1]);
+                o.y = pack_bf16x2(f[2], f[3]);
+                o.z = pack_bf16x2(f[4], f[5]);
+                o.w = pack_bf16x2(f[6], f[7]);
+                stg128(drow + gn, o);
+              } else {
+                if (crow) {
+                  const float4 cv = *reinterpret_cast<const float4*>(crow + gn);
+                  f[0] = fmaf(beta, cv.x, f[0]);
+                  f[1] = fmaf(beta, cv.y, f[1]);
+                  f[2] = fmaf(beta, cv.z, f[2]);
+                  f[3] = fmaf(beta, cv.w, f[3]);
+                }
+                *reinterpret_cast<float4*>(drow + gn) = make_float4(f[0], f[1], f[2], f[3]);
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+template <bool A_MN, bool B_MN, typename OutT, int BN>
+int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& args,
+                cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  auto kern = gemm_bf16_tc_kernel<A_MN, B_MN, OutT, BN>;
+  static bool attr_set = false;  // per template instantiation
+  if (!attr_set) {
+    B200_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int total = args.tiles_m * args.tiles_n * args.batch;
+  const int grid = total < num_sms() ? total : num_sms();
+  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, args);
+  B200_CHECK_CUDA(cudaGetLastError());
+  return B200_OK;
+}
+
+template <bool A_MN, bool B_MN>
+int dispatch_out(bool out_f32, int bn, const CUtensorMap& tmA, const CUtensorMap& tmB,
+                 const GemmArgs& args, cudaStream_t stream) {
+  if (out_f32) {
+    return bn == 256 ? launch_gemm<A_MN, B_MN, float, 256>(tmA, tmB, args, stream)
+                     : launch_gemm<A_MN, B_MN, float, 128>(tmA, tmB, args, stream);
+  }
+  return bn == 256 ? launch_gemm<A_MN, B_MN, __nv_bfloat16, 256>(tmA, tmB, args, stream)
+                   : launch_gemm<A_MN, B_MN, __nv_bfloat16, 128>(tmA, tmB, args, stream);
+}
+
+}  // namespace
+
+// Internal C++ entry (also used by the Newton-Schulz / Shampoo drivers).
+int gemm_bf16(bool a_mn, bool b_mn, int M, int N, int K, int batch, const void* A, long long lda,
+              long long strideA, const void* B, long long ldb, long long strideB, const void* C,
+              long long ldc, long long strideC, void* D, long long ldd, long long strideD,
+              bool out_f32, float alpha, float beta, const float* alpha_vec, const float* beta_vec,
+              int force_bn, cudaStream_t stream) {
+  B200_CHECK_ARG(M > 0 && N > 0 && K > 0 && batch > 0, "gemm: empty problem M=%d N=%d K=%d b=%d", M,
+                 N, K, batch);
+  B200_CHECK_ARG(N % 8 == 0, "gemm: N=%d must be a multiple of 8", N);
+  B200_CHECK_ARG(lda % 8 == 0 && ldb % 8 == 0, "gemm: lda=%lld ldb=%lld must be multiples of 8", lda,
+                 ldb);
+  const int out_vec = out_f32 ? 4 : 8;
+  B200_CHECK_ARG(ldd % out_vec == 0 && (C == nullptr || ldc % out_vec == 0),
+                 "gemm: ldd=%lld ldc=%lld must be multiples of %d", ldd, ldc, out_vec);
+  B200_CHECK_ARG((reinterpret_cast<uintptr_t>(D) & 15u) == 0 &&
+                     (reinterpret_cast<uintptr_t>(C) & 15u) == 0,
+                 "gemm: C/D must be 16-byte aligned");
+  B200_CHECK_ARG(strideA % 8 == 0 && strideB % 8 == 0 && strideD % out_vec == 0 &&
+                     strideC % out_vec == 0,
+                 "gemm: batch strides must keep 16-byte alignment");
+
+  // tile-N choice: 256 feeds the tensor pipe at full rate; fall back to 128 when the 256-wide
+  // grid would leave most SMs idle.
+  int bn = 256;
+  {
+    const long long t256 = (long long)((M + BM - 1) / BM) * ((N + 255) / 256) * batch;
+    if (N <= 128 || t256 < num_sms() / 2) bn = 128;
+  }
+  if (force_bn == 128 || force_bn == 256) bn = force_bn;
+
+  CUtensorMap tmA, tmB;
+  {
+    // A: K-major -> dims {K, M, batch}; MN-major -> dims {M, K, batch}
+    const uint64_t dims[3] = {(uint64_t)(a_mn ? M : K), (uint64_t)(a_mn ? K : M), (uint64_t)batch};
+    const uint64_t strides[2] = {(uint64_t)lda * 2, (uint64_t)(batch > 1 ? strideA : (long long)dims[1] * lda) * 2};
+    const uint32_t box[3] = {64, (uint32_t)(a_mn ? BK : BM), 1};
+    int rc = make_tensor_map(&tmA, A, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 3, dims, strides, box, true);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t dims[3] = {(uint64_t)(b_mn ? N : K), (uint64_t)(b_mn ? K : N), (uint64_t)batch};
+    const uint64_t strides[2] = {(uint64_t)ldb * 2, (uint64_t)(batch > 1 ? strideB : (long long)dims[1] * ldb) * 2};
+    const uint32_t box[3] = {64, (uint32_t)(b_mn ? BK : bn), 1};
+    int rc = make_tensor_map(&tmB, B, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 3, dims, strides, box, true);
+    if (rc) return rc;
+  }
+
+  GemmArgs args;
+  args.M = M;
+  args.N = N;
+  args.K = K;
+  args.batch = batch;
+  args.tiles_m = (M + BM - 1) / BM;
+  args.tiles_n = (N + bn - 1) / bn;
+  args.alpha = alpha;
+  args.beta = beta;
+  args.alpha_vec = alpha_vec;
+  args.beta_vec = beta_vec;
+  args.C = (beta != 0.0f) ? C : nullptr;
+  args.ldc = ldc;
+  args.strideC = strideC;
+  args.D = D;
+  args.ldd = ldd;
+  args.strideD = strideD;
+
+  if (!a_mn && !b_mn) return dispatch_out<false, false>(out_f32, bn, tmA, tmB, args, stream);
+  if (!a_mn && b_mn) return dispatch_out<false, true>(out_f32, bn, tmA, tmB, args, stream);
+  if (a_mn && b_mn) return dispatch_out<true, true>(out_f32, bn, tmA, tmB, args, stream);
+  return dispatch_out<true, false>(out_f32, bn, tmA, tmB, args, stream);
+}
+
+}  // namespace b200

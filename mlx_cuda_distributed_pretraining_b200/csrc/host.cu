@@ -1,0 +1,95 @@
+#include "host.h"
+
+#include <cudaTypedefs.h>
+#include <stdarg.h>
+#include <stdio.h>
+
+#include <mutex>
+
+namespace b200 {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+const char* last_error() { return g_err; }
+
+// cuTensorMapEncodeTiled is a driver entry point; resolve it through the runtime so the
+// library has no link-time dependency on libcuda (the CPU build box has no driver).
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) ==
+            cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess) {
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+    }
+  });
+  return fn;
+}
+
+int make_tensor_map(CUtensorMap* out, const void* base, CUtensorMapDataType dtype, int elem_bytes,
+                    int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                    const uint32_t* box, bool swizzle128) {
+  auto encode = get_encode();
+  if (!encode) {
+    set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+    return B200_ERR_CUDA;
+  }
+  if ((reinterpret_cast<uintptr_t>(base) & 15u) != 0) {
+    set_error("TMA base address %p is not 16-byte aligned", base);
+    return B200_ERR_ARG;
+  }
+  for (int i = 0; i + 1 < rank; ++i) {
+    if (strides_bytes[i] % 16 != 0) {
+      set_error("TMA stride[%d]=%llu bytes is not a multiple of 16", i,
+                (unsigned long long)strides_bytes[i]);
+      return B200_ERR_ARG;
+    }
+  }
+  if (swizzle128 && box[0] * (uint32_t)elem_bytes > 128) {
+    set_error("TMA inner box %u x %d B exceeds the 128-byte swizzle span", box[0], elem_bytes);
+    return B200_ERR_ARG;
+  }
+  cuuint64_t gdims[5];
+  cuuint64_t gstrides[4];
+  cuuint32_t gbox[5];
+  cuuint32_t estr[5];
+  for (int i = 0; i < rank; ++i) {
+    gdims[i] = dims[i];
+    gbox[i] = box[i];
+    estr[i] = 1;
+    if (i + 1 < rank) gstrides[i] = strides_bytes[i];
+  }
+  CUresult r = encode(out, dtype, (cuuint32_t)rank, const_cast<void*>(base), gdims, gstrides, gbox,
+                      estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d dims %llu,%llu box %u,%u)",
+              (int)r, rank, (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0),
+              box[0], rank > 1 ? box[1] : 0);
+    return B200_ERR_CUDA;
+  }
+  return B200_OK;
+}
+
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+  }
+  return n;
+}
+
+}  // namespace b200

@@ -1,0 +1,44 @@
+// Host-side helpers shared by the C-ABI entry points: error reporting and TMA tensor maps.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/b200_hotpath.h"
+
+namespace b200 {
+
+// thread-local last error message (returned by b200_last_error())
+void set_error(const char* fmt, ...);
+const char* last_error();
+
+// error codes: B200_OK / B200_ERR_* macros from the public header
+
+#define B200_CHECK_ARG(cond, ...)          \
+  do {                                     \
+    if (!(cond)) {                         \
+      ::b200::set_error(__VA_ARGS__);      \
+      return B200_ERR_ARG;         \
+    }                                      \
+  } while (0)
+
+#define B200_CHECK_CUDA(expr)                                                              \
+  do {                                                                                     \
+    cudaError_t e__ = (expr);                                                              \
+    if (e__ != cudaSuccess) {                                                              \
+      ::b200::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, \
+                        __LINE__);                                                         \
+      return B200_ERR_CUDA;                                                        \
+    }                                                                                      \
+  } while (0)
+
+// Builds a tiled tensor map with 128B swizzle over a row-major array of `elem_bytes`-sized
+// elements. dims/strides are listed innermost-first; strides_bytes[i] is the byte stride of
+// dims[i+1] (rank-1 entries). Returns 0 on success.
+int make_tensor_map(CUtensorMap* out, const void* base, CUtensorMapDataType dtype, int elem_bytes,
+                    int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                    const uint32_t* box, bool swizzle128);
+
+int num_sms();
+
+}  // namespace b200

@@ -1,0 +1,84 @@
+// Newton-Schulz orthogonalisation driver (reference: Muon.zeropower_via_newtonschulz5,
+// optimizers/muon.py:54-83):   X0 = G/(||G||_F+eps);  repeat: A = X X^T, B = bA + cAA, X = aX + BX
+//
+// B200 formulation: every step is a batched tcgen05 GEMM with a fused epilogue
+//   G1: A  = X X^T                (wide)   |  A = X^T X   (tall, both operands MN-major)
+//   G2: B  = b*A + c*(A A)        (A symmetric -> A A^T, both operands K-major)
+//   G3: X' = a*X + B X            (wide, X as MN-major B operand) | X' = a*X + X B (tall)
+// so the reference's transpose for tall matrices (muon.py:68-70,80-81) never materialises, and
+// the normalisation X0 = G/(||G||+eps) is folded into the first iteration's epilogue scalars
+// (per-matrix 1/(norm+eps) vectors produced by the momentum kernel's fused sum of squares).
+#include "host.h"
+
+namespace b200 {
+
+int gemm_bf16(bool a_mn, bool b_mn, int M, int N, int K, int batch, const void* A, long long lda,
+              long long strideA, const void* B, long long ldb, long long strideB, const void* C,
+              long long ldc, long long strideC, void* D, long long ldd, long long strideD,
+              bool out_f32, float alpha, float beta, const float* alpha_vec, const float* beta_vec,
+              int force_bn, cudaStream_t stream);
+
+static inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
+
+size_t newton_schulz_workspace_bytes(int batch, int rows, int cols, int steps) {
+  const size_t m = rows < cols ? rows : cols;
+  size_t bytes = 2 * align256((size_t)batch * m * m * 2);
+  if (steps >= 2) bytes += align256((size_t)batch * rows * cols * 2);
+  return bytes;
+}
+
+int newton_schulz(const void* x_in, void* x_out, int batch, int rows, int cols, int steps, float a,
+                  float b, float c, const float* inv_norm, const float* inv_norm_sq, void* ws,
+                  size_t ws_bytes, cudaStream_t stream) {
+  B200_CHECK_ARG(batch > 0 && rows > 0 && cols > 0 && steps > 0,
+                 "newton_schulz: bad shape batch=%d rows=%d cols=%d steps=%d", batch, rows, cols,
+                 steps);
+  B200_CHECK_ARG(cols % 8 == 0, "newton_schulz: cols=%d must be a multiple of 8 (16-byte rows)",
+                 cols);
+  B200_CHECK_ARG(x_in != x_out, "newton_schulz: x_in and x_out must be distinct buffers");
+  if (ws_bytes < newton_schulz_workspace_bytes(batch, rows, cols, steps)) {
+    set_error("newton_schulz: workspace too small (%zu < %zu)", ws_bytes,
+              newton_schulz_workspace_bytes(batch, rows, cols, steps));
+    return B200_ERR_WORKSPACE;
+  }
+  const bool tall = rows > cols;
+  const int m = tall ? cols : rows;
+  const long long mm = (long long)m * m;
+  const long long rc = (long long)rows * cols;
+  char* w = reinterpret_cast<char*>(ws);
+  void* Abuf = w;
+  void* Bbuf = w + align256((size_t)batch * mm * 2);
+  void* Xtmp = w + 2 * align256((size_t)batch * mm * 2);
+
+  const void* cur = x_in;
+  for (int it = 0; it < steps; ++it) {
+    void* nxt = ((steps - 1 - it) % 2 == 0) ? x_out : Xtmp;
+    const float* s1 = (it == 0) ? inv_norm : nullptr;
+    const float* s2 = (it == 0) ? inv_norm_sq : nullptr;
+    int rc_;
+    // G1
+    if (!tall)
+      rc_ = gemm_bf16(false, false, m, m, cols, batch, cur, cols, rc, cur, cols, rc, nullptr, 0, 0,
+                      Abuf, m, mm, false, 1.0f, 0.0f, s2, nullptr, 0, stream);
+    else
+      rc_ = gemm_bf16(true, true, m, m, rows, batch, cur, cols, rc, cur, cols, rc, nullptr, 0, 0,
+                      Abuf, m, mm, false, 1.0f, 0.0f, s2, nullptr, 0, stream);
+    if (rc_) return rc_;
+    // G2: B = b*A + c*A*A
+    rc_ = gemm_bf16(false, false, m, m, m, batch, Abuf, m, mm, Abuf, m, mm, Abuf, m, mm, Bbuf, m,
+                    mm, false, c, b, nullptr, nullptr, 0, stream);
+    if (rc_) return rc_;
+    // G3
+    if (!tall)
+      rc_ = gemm_bf16(false, true, m, cols, m, batch, Bbuf, m, mm, cur, cols, rc, cur, cols, rc,
+                      nxt, cols, rc, false, 1.0f, a, s1, s1, 0, stream);
+    else
+      rc_ = gemm_bf16(false, false, rows, m, m, batch, cur, cols, rc, Bbuf, m, mm, cur, cols, rc,
+                      nxt, cols, rc, false, 1.0f, a, s1, s1, 0, stream);
+    if (rc_) return rc_;
+    cur = nxt;
+  }
+  return B200_OK;
+}
+
+}  // namespace b200

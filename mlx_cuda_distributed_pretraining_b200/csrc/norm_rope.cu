@@ -1,0 +1,255 @@
+// RMSNorm (arch/llama.py:50-56 of the reference) and interleaved-pair RoPE
+// (arch/llama_standard.py:74-75,117-127) as single-pass vectorised HBM kernels, forward + backward.
+#include "common.cuh"
+#include "host.h"
+
+namespace b200 {
+
+namespace {
+
+constexpr int RN_THREADS = 128;
+constexpr int RN_MAX_VEC = 8;  // per-thread 8-element vectors held in registers -> H <= 8192
+
+__device__ __forceinline__ void ld8(const __nv_bfloat16* p, float* f) {
+  const uint4 a = *reinterpret_cast<const uint4*>(p);
+  const float2 v0 = unpack_bf16x2(a.x), v1 = unpack_bf16x2(a.y), v2 = unpack_bf16x2(a.z),
+               v3 = unpack_bf16x2(a.w);
+  f[0] = v0.x; f[1] = v0.y; f[2] = v1.x; f[3] = v1.y;
+  f[4] = v2.x; f[5] = v2.y; f[6] = v3.x; f[7] = v3.y;
+}
+__device__ __forceinline__ void ld8(const float* p, float* f) {
+  const float4 a = *reinterpret_cast<const float4*>(p);
+  const float4 b = *reinterpret_cast<const float4*>(p + 4);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w;
+  f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+__device__ __forceinline__ void st8(__nv_bfloat16* p, const float* f) {
+  uint4 o;
+  o.x = pack_bf16x2(f[0], f[1]);
+  o.y = pack_bf16x2(f[2], f[3]);
+  o.z = pack_bf16x2(f[4], f[5]);
+  o.w = pack_bf16x2(f[6], f[7]);
+  *reinterpret_cast<uint4*>(p) = o;
+}
+__device__ __forceinline__ void st8(float* p, const float* f) {
+  *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(f[4], f[5], f[6], f[7]);
+}
+
+__device__ __forceinline__ float block_sum_128(float v, float* red) {
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  const float t = red[0] + red[1] + red[2] + red[3];
+  __syncthreads();
+  return t;
+}
+
+template <typename T, int NV>
+__global__ void __launch_bounds__(RN_THREADS)
+rmsnorm_fwd_kernel(const T* __restrict__ x, const T* __restrict__ w, T* __restrict__ y,
+                   float* __restrict__ rstd_out, int rows, int H, float eps) {
+  __shared__ float red[4];
+  float wv[NV][8];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const int col = (v * RN_THREADS + threadIdx.x) * 8;
+    if (col < H) ld8(w + col, wv[v]);
+  }
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    const T* xr = x + (long long)row * H;
+    float xv[NV][8];
+    float ss = 0.f;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      const int col = (v * RN_THREADS + threadIdx.x) * 8;
+      if (col < H) {
+        ld8(xr + col, xv[v]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ss += xv[v][j] * xv[v][j];
+      }
+    }
+    const float tot = block_sum_128(ss, red);
+    // reference: x / sqrt(mean(x^2) + eps) * w, all in fp32, cast back to the input dtype
+    const float rstd = 1.0f / sqrtf(tot / (float)H + eps);
+    if (threadIdx.x == 0 && rstd_out) rstd_out[row] = rstd;
+    T* yr = y + (long long)row * H;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      const int col = (v * RN_THREADS + threadIdx.x) * 8;
+      if (col < H) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = xv[v][j] * rstd * wv[v][j];
+        st8(yr + col, o);
+      }
+    }
+  }
+}
+
+// dx = rstd * (dy*w - x * rstd^2 * mean(dy*w*x)) ; dw += dy * x * rstd  (fp32 atomics, one per
+// column per block)
+template <typename T, int NV>
+__global__ void __launch_bounds__(RN_THREADS)
+rmsnorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ w,
+                   const float* __restrict__ rstd_in, T* __restrict__ dx, float* __restrict__ dw,
+                   int rows, int H) {
+  __shared__ float red[4];
+  float wv[NV][8], dwv[NV][8];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const int col = (v * RN_THREADS + threadIdx.x) * 8;
+    if (col < H) ld8(w + col, wv[v]);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dwv[v][j] = 0.f;
+  }
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    const T* xr = x + (long long)row * H;
+    const T* dyr = dy + (long long)row * H;
+    const float rstd = rstd_in[row];
+    float xv[NV][8], gv[NV][8];
+    float dot = 0.f;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      const int col = (v * RN_THREADS + threadIdx.x) * 8;
+      if (col < H) {
+        ld8(xr + col, xv[v]);
+        ld8(dyr + col, gv[v]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          dwv[v][j] += gv[v][j] * xv[v][j] * rstd;
+          gv[v][j] *= wv[v][j];
+          dot += gv[v][j] * xv[v][j];
+        }
+      }
+    }
+    const float tot = block_sum_128(dot, red);
+    const float c = tot / (float)H * rstd * rstd;
+    T* dxr = dx + (long long)row * H;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      const int col = (v * RN_THREADS + threadIdx.x) * 8;
+      if (col < H) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = rstd * (gv[v][j] - xv[v][j] * c);
+        st8(dxr + col, o);
+      }
+    }
+  }
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const int col = (v * RN_THREADS + threadIdx.x) * 8;
+    if (col < H) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) atomicAdd(dw + col + j, dwv[v][j]);
+    }
+  }
+}
+
+// x: [B, S, NH, D]; cos/sin: [S, D/2] fp32. out[2i] = x[2i]*c - x[2i+1]*s ; out[2i+1] = x[2i]*s +
+// x[2i+1]*c. The backward pass is the same rotation with sign = -1.
+template <typename T>
+__global__ void __launch_bounds__(256)
+rope_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __restrict__ cos_t,
+            const float* __restrict__ sin_t, long long nvec, int S, int NH, int D, float sign) {
+  const int vec_per_head = D / 8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int dv = (int)(i % vec_per_head);
+    const long long t = i / vec_per_head / NH;  // token index b*S + s
+    const int s = (int)(t % S);
+    float xv[8], o[8];
+    ld8(x + i * 8, xv);
+    const float4 c = *reinterpret_cast<const float4*>(cos_t + (long long)s * (D / 2) + dv * 4);
+    float4 sn = *reinterpret_cast<const float4*>(sin_t + (long long)s * (D / 2) + dv * 4);
+    sn.x *= sign; sn.y *= sign; sn.z *= sign; sn.w *= sign;
+    o[0] = xv[0] * c.x - xv[1] * sn.x;  o[1] = xv[0] * sn.x + xv[1] * c.x;
+    o[2] = xv[2] * c.y - xv[3] * sn.y;  o[3] = xv[2] * sn.y + xv[3] * c.y;
+    o[4] = xv[4] * c.z - xv[5] * sn.z;  o[5] = xv[4] * sn.z + xv[5] * c.z;
+    o[6] = xv[6] * c.w - xv[7] * sn.w;  o[7] = xv[6] * sn.w + xv[7] * c.w;
+    st8(y + i * 8, o);
+  }
+}
+
+template <typename T>
+int rmsnorm_fwd_t(const T* x, const T* w, T* y, float* rstd, int rows, int H, float eps,
+                  cudaStream_t stream) {
+  const int nv = (H / 8 + RN_THREADS - 1) / RN_THREADS;
+  const int grid = rows < num_sms() * 16 ? rows : num_sms() * 16;
+  switch (nv) {
+    case 1: rmsnorm_fwd_kernel<T, 1><<<grid, RN_THREADS, 0, stream>>>(x, w, y, rstd, rows, H, eps); break;
+    case 2: rmsnorm_fwd_kernel<T, 2><<<grid, RN_THREADS, 0, stream>>>(x, w, y, rstd, rows, H, eps); break;
+    case 3: case 4: rmsnorm_fwd_kernel<T, 4><<<grid, RN_THREADS, 0, stream>>>(x, w, y, rstd, rows, H, eps); break;
+    default: rmsnorm_fwd_kernel<T, RN_MAX_VEC><<<grid, RN_THREADS, 0, stream>>>(x, w, y, rstd, rows, H, eps); break;
+  }
+  B200_CHECK_CUDA(cudaGetLastError());
+  return B200_OK;
+}
+
+template <typename T>
+int rmsnorm_bwd_t(const T* dy, const T* x, const T* w, const float* rstd, T* dx, float* dw,
+                  int rows, int H, cudaStream_t stream) {
+  const int nv = (H / 8 + RN_THREADS - 1) / RN_THREADS;
+  const int grid = rows < num_sms() * 4 ? rows : num_sms() * 4;
+  switch (nv) {
+    case 1: rmsnorm_bwd_kernel<T, 1><<<grid, RN_THREADS, 0, stream>>>(dy, x, w, rstd, dx, dw, rows, H); break;
+    case 2: rmsnorm_bwd_kernel<T, 2><<<grid, RN_THREADS, 0, stream>>>(dy, x, w, rstd, dx, dw, rows, H); break;
+    case 3: case 4: rmsnorm_bwd_kernel<T, 4><<<grid, RN_THREADS, 0, stream>>>(dy, x, w, rstd, dx, dw, rows, H); break;
+    default: rmsnorm_bwd_kernel<T, RN_MAX_VEC><<<grid, RN_THREADS, 0, stream>>>(dy, x, w, rstd, dx, dw, rows, H); break;
+  }
+  B200_CHECK_CUDA(cudaGetLastError());
+  return B200_OK;
+}
+
+inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace
+
+int rmsnorm_fwd(const void* x, const void* w, void* y, float* rstd, int rows, int H, float eps,
+                int is_bf16, cudaStream_t stream) {
+  B200_CHECK_ARG(rows > 0 && H > 0 && H % 8 == 0 && H <= RN_THREADS * 8 * RN_MAX_VEC,
+                 "rmsnorm_fwd: unsupported shape rows=%d H=%d (H %% 8 == 0, H <= %d)", rows, H,
+                 RN_THREADS * 8 * RN_MAX_VEC);
+  B200_CHECK_ARG(al16(x) && al16(w) && al16(y), "rmsnorm_fwd: 16-byte alignment required");
+  if (is_bf16)
+    return rmsnorm_fwd_t<__nv_bfloat16>((const __nv_bfloat16*)x, (const __nv_bfloat16*)w,
+                                        (__nv_bfloat16*)y, rstd, rows, H, eps, stream);
+  return rmsnorm_fwd_t<float>((const float*)x, (const float*)w, (float*)y, rstd, rows, H, eps,
+                              stream);
+}
+
+int rmsnorm_bwd(const void* dy, const void* x, const void* w, const float* rstd, void* dx,
+                float* dw, int rows, int H, int is_bf16, cudaStream_t stream) {
+  B200_CHECK_ARG(rows > 0 && H > 0 && H % 8 == 0 && H <= RN_THREADS * 8 * RN_MAX_VEC,
+                 "rmsnorm_bwd: unsupported shape rows=%d H=%d", rows, H);
+  B200_CHECK_ARG(al16(dy) && al16(x) && al16(w) && al16(dx), "rmsnorm_bwd: alignment");
+  B200_CHECK_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * H, stream));
+  if (is_bf16)
+    return rmsnorm_bwd_t<__nv_bfloat16>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x,
+                                        (const __nv_bfloat16*)w, rstd, (__nv_bfloat16*)dx, dw,
+                                        rows, H, stream);
+  return rmsnorm_bwd_t<float>((const float*)dy, (const float*)x, (const float*)w, rstd, (float*)dx,
+                              dw, rows, H, stream);
+}
+
+int rope(const void* x, void* y, const float* cos_t, const float* sin_t, int B, int S, int NH,
+         int D, int backward, int is_bf16, cudaStream_t stream) {
+  B200_CHECK_ARG(B > 0 && S > 0 && NH > 0 && D > 0 && D % 8 == 0, "rope: D=%d must be a multiple of 8",
+                 D);
+  B200_CHECK_ARG(al16(x) && al16(y) && al16(cos_t) && al16(sin_t), "rope: alignment");
+  const long long nvec = (long long)B * S * NH * D / 8;
+  long long blocks = (nvec + 255) / 256;
+  if (blocks > (long long)num_sms() * 8) blocks = (long long)num_sms() * 8;
+  const float sign = backward ? -1.0f : 1.0f;
+  if (is_bf16)
+    rope_kernel<__nv_bfloat16><<<(int)blocks, 256, 0, stream>>>(
+        (const __nv_bfloat16*)x, (__nv_bfloat16*)y, cos_t, sin_t, nvec, S, NH, D, sign);
+  else
+    rope_kernel<float><<<(int)blocks, 256, 0, stream>>>((const float*)x, (float*)y, cos_t, sin_t,
+                                                        nvec, S, NH, D, sign);
+  B200_CHECK_CUDA(cudaGetLastError());
+  return B200_OK;
+}
+
+}  // namespace b200

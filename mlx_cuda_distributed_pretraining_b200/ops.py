@@ -1,0 +1,346 @@
+"""PyTorch-tensor wrappers over the C ABI (include/b200_hotpath.h).
+
+PyTorch is plumbing here: it owns device memory and streams; all arithmetic below runs in the
+hand-written sm_100a kernels.  Every wrapper validates dtype/contiguity and raises on failure --
+there is no eager fallback.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from ._lib import B200Error, check, lib, require_device
+
+NS_COEFFS = (3.4445, -4.7750, 2.0315)  # optimizers/muon.py:65
+NS_EPS = 1e-7                          # optimizers/muon.py:73
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _need(t: torch.Tensor, dtype, name: str) -> None:
+    if not t.is_cuda:
+        raise B200Error(f"{name}: expected a CUDA tensor (no CPU fallback)")
+    if t.dtype != dtype:
+        raise ValueError(f"{name}: expected {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name}: tensor must be contiguous")
+
+
+def _is_bf16(t: torch.Tensor, name: str) -> int:
+    if t.dtype == torch.bfloat16:
+        return 1
+    if t.dtype == torch.float32:
+        return 0
+    raise ValueError(f"{name}: unsupported dtype {t.dtype} (bf16 or fp32)")
+
+
+# ------------------------------------------------------------------------------------------------
+# dense contraction engine
+# ------------------------------------------------------------------------------------------------
+def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = False,
+         c: Optional[torch.Tensor] = None, alpha: float = 1.0, beta: float = 0.0,
+         alpha_vec: Optional[torch.Tensor] = None, beta_vec: Optional[torch.Tensor] = None,
+         out: Optional[torch.Tensor] = None, out_dtype: torch.dtype = torch.bfloat16,
+         force_bn: int = 0) -> torch.Tensor:
+    """D = alpha*op(A) op(B) + beta*C, batched over a leading dim.
+
+    a: [.., M, K] (a_mn=False) or [.., K, M] (a_mn=True); b: [.., N, K] or [.., K, N] (b_mn=True).
+    """
+    _need(a, torch.bfloat16, "a")
+    _need(b, torch.bfloat16, "b")
+    a3 = a if a.dim() == 3 else a.unsqueeze(0)
+    b3 = b if b.dim() == 3 else b.unsqueeze(0)
+    batch = a3.shape[0]
+    if b3.shape[0] != batch:
+        raise ValueError("gemm: batch mismatch")
+    (K, M) = a3.shape[1:] if a_mn else a3.shape[1:][::-1]
+    (Kb, N) = b3.shape[1:] if b_mn else b3.shape[1:][::-1]
+    if K != Kb:
+        raise ValueError(f"gemm: K mismatch {K} vs {Kb}")
+    if out is None:
+        out = torch.empty((batch, M, N), device=a.device, dtype=out_dtype)
+    out_f32 = _is_bf16(out, "out") == 0
+    if tuple(out.shape[-2:]) != (M, N) or not out.is_contiguous():
+        raise ValueError("gemm: bad out tensor")
+    if c is not None:
+        if c.dtype != out.dtype or tuple(c.shape[-2:]) != (M, N) or not c.is_contiguous():
+            raise ValueError("gemm: c must match out dtype/shape and be contiguous")
+    for v, nm in ((alpha_vec, "alpha_vec"), (beta_vec, "beta_vec")):
+        if v is not None:
+            _need(v, torch.float32, nm)
+            if v.numel() != batch:
+                raise ValueError(f"gemm: {nm} must have one entry per batch")
+    rc = lib().b200_gemm_bf16(
+        int(a_mn), int(b_mn), M, N, K, batch,
+        a3.data_ptr(), a3.shape[2], a3.shape[1] * a3.shape[2],
+        b3.data_ptr(), b3.shape[2], b3.shape[1] * b3.shape[2],
+        _ptr(c), N, M * N,
+        out.data_ptr(), N, M * N,
+        int(out_f32), float(alpha), float(beta), _ptr(alpha_vec), _ptr(beta_vec), int(force_bn),
+        _stream())
+    check(rc, "b200_gemm_bf16")
+    return out.view(M, N) if (a.dim() == 2 and out.dim() == 3) else out
+
+
+# ------------------------------------------------------------------------------------------------
+# Newton-Schulz / Muon pieces
+# ------------------------------------------------------------------------------------------------
+def ns_workspace_bytes(batch: int, rows: int, cols: int, steps: int) -> int:
+    return int(lib().b200_newton_schulz_workspace_bytes(batch, rows, cols, steps))
+
+
+def sumsq(x: torch.Tensor, out: Optional[torch.Tensor] = None, zero_first: bool = True) -> torch.Tensor:
+    """Per-matrix sum of squares of x [batch, ...] -> fp32 [batch]."""
+    xb = x if x.dim() >= 2 else x.unsqueeze(0)
+    batch = xb.shape[0] if x.dim() == 3 else 1
+    numel = x.numel() // batch
+    if out is None:
+        out = torch.empty(batch, device=x.device, dtype=torch.float32)
+    check(lib().b200_sumsq(x.data_ptr(), _is_bf16(x, "x"), out.data_ptr(), numel, batch,
+                           int(zero_first), _stream()), "b200_sumsq")
+    return out
+
+
+def ns_scales(ss: torch.Tensor, eps: float = NS_EPS) -> Tuple[torch.Tensor, torch.Tensor]:
+    inv = torch.empty_like(ss)
+    inv2 = torch.empty_like(ss)
+    check(lib().b200_ns_scales(ss.data_ptr(), inv.data_ptr(), inv2.data_ptr(), ss.numel(), eps,
+                               _stream()), "b200_ns_scales")
+    return inv, inv2
+
+
+def newton_schulz_raw(x_in: torch.Tensor, x_out: torch.Tensor, inv_norm: torch.Tensor,
+                      inv_norm_sq: torch.Tensor, workspace: torch.Tensor, steps: int = 5,
+                      coeffs: Sequence[float] = NS_COEFFS) -> torch.Tensor:
+    """x_in/x_out: bf16 [batch, rows, cols]; workspace: uint8 buffer from ns_workspace_bytes."""
+    _need(x_in, torch.bfloat16, "x_in")
+    _need(x_out, torch.bfloat16, "x_out")
+    batch, rows, cols = x_in.shape
+    a, b, c = coeffs
+    check(lib().b200_newton_schulz(x_in.data_ptr(), x_out.data_ptr(), batch, rows, cols, steps,
+                                   float(a), float(b), float(c), inv_norm.data_ptr(),
+                                   inv_norm_sq.data_ptr(), workspace.data_ptr(),
+                                   workspace.numel() * workspace.element_size(), _stream()),
+          "b200_newton_schulz")
+    return x_out
+
+
+def zeropower_via_newtonschulz5(g: torch.Tensor, steps: int = 5, eps: float = NS_EPS,
+                                coeffs: Sequence[float] = NS_COEFFS) -> torch.Tensor:
+    """Drop-in for Muon.zeropower_via_newtonschulz5 (optimizers/muon.py:54-83).
+
+    g: [rows, cols] or [batch, rows, cols], fp32 or bf16 on a B200. Returns bf16 of the same shape.
+    """
+    require_device()
+    squeeze = g.dim() == 2
+    g3 = (g.unsqueeze(0) if squeeze else g).contiguous()
+    batch, rows, cols = g3.shape
+    x_in = g3 if g3.dtype == torch.bfloat16 else g3.to(torch.bfloat16)
+    # Frobenius norm of the (fp32) input, folded into iteration 1 by the kernel
+    inv, inv2 = ns_scales(sumsq(g3 if g3.dtype in (torch.float32, torch.bfloat16) else x_in), eps)
+    ws = torch.empty(ns_workspace_bytes(batch, rows, cols, steps), device=g.device, dtype=torch.uint8)
+    x_out = torch.empty_like(x_in)
+    newton_schulz_raw(x_in, x_out, inv, inv2, ws, steps, coeffs)
+    return x_out[0] if squeeze else x_out
+
+
+def muon_momentum(g: torch.Tensor, buf: torch.Tensor, u: torch.Tensor, sumsq_out: torch.Tensor,
+                  mu: float, nesterov: bool, gscale: float = 1.0) -> None:
+    """g,buf,u: [batch, rows, cols] (g bf16|fp32, buf fp32, u bf16); sumsq_out fp32 [batch]."""
+    _need(buf, torch.float32, "buf")
+    _need(u, torch.bfloat16, "u")
+    batch = g.shape[0] if g.dim() == 3 else 1
+    numel = g.numel() // batch
+    check(lib().b200_muon_momentum(g.data_ptr(), _is_bf16(g, "g"), buf.data_ptr(), u.data_ptr(),
+                                   sumsq_out.data_ptr(), numel, batch, float(mu), int(nesterov),
+                                   float(gscale), _stream()), "b200_muon_momentum")
+
+
+def axpy_update(p32: torch.Tensor, p16: Optional[torch.Tensor], x: torch.Tensor, s: float) -> None:
+    _need(p32, torch.float32, "p32")
+    check(lib().b200_axpy_update(p32.data_ptr(), _ptr(p16), x.data_ptr(), _is_bf16(x, "x"),
+                                 p32.numel(), float(s), _stream()), "b200_axpy_update")
+
+
+def sgd_momentum(p32, p16, g, buf, mu: float, nesterov: bool, lr: float, gscale: float = 1.0) -> None:
+    check(lib().b200_sgd_momentum(p32.data_ptr(), _ptr(p16), g.data_ptr(), _is_bf16(g, "g"),
+                                  buf.data_ptr(), p32.numel(), float(mu), int(nesterov), float(lr),
+                                  float(gscale), _stream()), "b200_sgd_momentum")
+
+
+def adamw(p32, p16, g, m, v, lr: float, b1: float, b2: float, eps: float, wd: float,
+          bc1: float = 1.0, bc2: float = 1.0, gscale: float = 1.0) -> None:
+    check(lib().b200_adamw(p32.data_ptr(), _ptr(p16), g.data_ptr(), _is_bf16(g, "g"), m.data_ptr(),
+                           v.data_ptr(), p32.numel(), float(lr), float(b1), float(b2), float(eps),
+                           float(wd), float(bc1), float(bc2), float(gscale), _stream()),
+          "b200_adamw")
+
+
+def adam_direction(d, g, m, v, lr, b1, b2, eps, bc1=1.0, bc2=1.0, gscale=1.0) -> None:
+    check(lib().b200_adam_direction(d.data_ptr(), g.data_ptr(), _is_bf16(g, "g"), m.data_ptr(),
+                                    v.data_ptr(), d.numel(), float(lr), float(b1), float(b2),
+                                    float(eps), float(bc1), float(bc2), float(gscale), _stream()),
+          "b200_adam_direction")
+
+
+def clip_accum(g: torch.Tensor, acc: torch.Tensor, clip: float, scale: float, init: bool) -> None:
+    _need(acc, torch.float32, "acc")
+    check(lib().b200_clip_accum(g.data_ptr(), _is_bf16(g, "g"), acc.data_ptr(), g.numel(),
+                                float(clip), float(scale), int(init), _stream()), "b200_clip_accum")
+
+
+def split_bf16(src: torch.Tensor, rows: int, cols: int, hi: torch.Tensor,
+               lo: Optional[torch.Tensor], scale: float = 1.0, diag_add: float = 0.0) -> None:
+    """hi(+lo) = bf16 split of (src[:rows,:cols] + diag_add*I)*scale; src fp32 2-D (strided rows)."""
+    _need(hi, torch.bfloat16, "hi")
+    check(lib().b200_split_bf16(src.data_ptr(), src.stride(0), hi.data_ptr(), _ptr(lo),
+                                hi.stride(0), rows, cols, float(scale), float(diag_add), _stream()),
+          "b200_split_bf16")
+
+
+# ------------------------------------------------------------------------------------------------
+# RMSNorm / RoPE / attention as autograd functions
+# ------------------------------------------------------------------------------------------------
+class _RMSNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, eps):
+        xs = x.contiguous()
+        rows, H = xs.numel() // xs.shape[-1], xs.shape[-1]
+        y = torch.empty_like(xs)
+        rstd = torch.empty(rows, device=x.device, dtype=torch.float32)
+        wc = w.contiguous().to(xs.dtype)
+        check(lib().b200_rmsnorm_fwd(xs.data_ptr(), wc.data_ptr(), y.data_ptr(), rstd.data_ptr(),
+                                     rows, H, float(eps), _is_bf16(xs, "x"), _stream()),
+              "b200_rmsnorm_fwd")
+        ctx.save_for_backward(xs, wc, rstd)
+        ctx.w_dtype = w.dtype
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xs, wc, rstd = ctx.saved_tensors
+        dy = dy.contiguous()
+        rows, H = xs.numel() // xs.shape[-1], xs.shape[-1]
+        dx = torch.empty_like(xs)
+        dw = torch.empty(H, device=xs.device, dtype=torch.float32)
+        check(lib().b200_rmsnorm_bwd(dy.data_ptr(), xs.data_ptr(), wc.data_ptr(), rstd.data_ptr(),
+                                     dx.data_ptr(), dw.data_ptr(), rows, H, _is_bf16(xs, "x"),
+                                     _stream()), "b200_rmsnorm_bwd")
+        return dx, dw.to(ctx.w_dtype), None
+
+
+def rmsnorm(x: torch.Tensor, w: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
+    return _RMSNormFn.apply(x, w, eps)
+
+
+def rope_tables(seq_len: int, head_dim: int, theta: float, device) -> Tuple[torch.Tensor, torch.Tensor]:
+    """cos/sin [S, D/2] fp32: angle = pos * theta^(-2i/D) (arch/llama_standard.py:74-75,83-84)."""
+    freqs = torch.pow(torch.tensor(float(theta), dtype=torch.float32),
+                      -torch.arange(0, head_dim, 2, dtype=torch.float32) / head_dim)
+    ang = torch.outer(torch.arange(seq_len, dtype=torch.float32), freqs)
+    return torch.cos(ang).to(device).contiguous(), torch.sin(ang).to(device).contiguous()
+
+
+class _RopeFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, cos_t, sin_t):
+        xs = x.contiguous()
+        B, S, NH, D = xs.shape
+        y = torch.empty_like(xs)
+        check(lib().b200_rope(xs.data_ptr(), y.data_ptr(), cos_t.data_ptr(), sin_t.data_ptr(), B, S,
+                              NH, D, 0, _is_bf16(xs, "x"), _stream()), "b200_rope")
+        ctx.save_for_backward(cos_t, sin_t)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        cos_t, sin_t = ctx.saved_tensors
+        dy = dy.contiguous()
+        B, S, NH, D = dy.shape
+        dx = torch.empty_like(dy)
+        check(lib().b200_rope(dy.data_ptr(), dx.data_ptr(), cos_t.data_ptr(), sin_t.data_ptr(), B, S,
+                              NH, D, 1, _is_bf16(dy, "dy"), _stream()), "b200_rope(bwd)")
+        return dx, None, None
+
+
+def rope(x: torch.Tensor, cos_t: torch.Tensor, sin_t: torch.Tensor) -> torch.Tensor:
+    """x: [B, S, heads, D]; interleaved-pair rotation."""
+    return _RopeFn.apply(x, cos_t, sin_t)
+
+
+def _pad_head_dim(D: int) -> int:
+    if D <= 64:
+        return 64
+    if D <= 128:
+        return 128
+    raise ValueError(f"attention: head_dim {D} > 128 is not supported")
+
+
+def attention_fwd_raw(q, k, v, scale: float, causal: bool):
+    """q [B,S,H,D], k/v [B,S,Hk,D] bf16 contiguous, D in {64,128}. Returns (o, lse[B,H,S])."""
+    for t, nm in ((q, "q"), (k, "k"), (v, "v")):
+        _need(t, torch.bfloat16, nm)
+    B, S, H, D = q.shape
+    Hk = k.shape[2]
+    o = torch.empty_like(q)
+    lse = torch.empty((B, H, S), device=q.device, dtype=torch.float32)
+    check(lib().b200_attn_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), lse.data_ptr(),
+                              B, S, H, Hk, D, float(scale), int(causal), _stream()), "b200_attn_fwd")
+    return o, lse
+
+
+def attention_bwd_raw(q, k, v, o, do, lse, scale: float, causal: bool):
+    B, S, H, D = q.shape
+    Hk = k.shape[2]
+    dq = torch.empty_like(q)
+    dk = torch.empty_like(k)
+    dv = torch.empty_like(v)
+    nbytes = int(lib().b200_attn_bwd_workspace_bytes(B, S, H, Hk, D))
+    ws = torch.empty(max(nbytes, 16), device=q.device, dtype=torch.uint8)
+    check(lib().b200_attn_bwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), do.data_ptr(),
+                              lse.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), B, S, H,
+                              Hk, D, float(scale), int(causal), ws.data_ptr(), ws.numel(), _stream()),
+          "b200_attn_bwd")
+    return dq, dk, dv
+
+
+class _AttentionFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q, k, v, scale, causal):
+        D = q.shape[-1]
+        Dp = _pad_head_dim(D)
+        if Dp != D:  # zero-padding the head dim leaves QK^T and the first D columns of PV unchanged
+            q, k, v = (torch.nn.functional.pad(t, (0, Dp - D)) for t in (q, k, v))
+        q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
+        o, lse = attention_fwd_raw(q, k, v, scale, causal)
+        ctx.save_for_backward(q, k, v, o, lse)
+        ctx.scale, ctx.causal, ctx.D = scale, causal, D
+        return o[..., :D] if Dp != D else o
+
+    @staticmethod
+    def backward(ctx, do):
+        q, k, v, o, lse = ctx.saved_tensors
+        Dp = q.shape[-1]
+        if Dp != ctx.D:
+            do = torch.nn.functional.pad(do, (0, Dp - ctx.D))
+        do = do.contiguous()
+        dq, dk, dv = attention_bwd_raw(q, k, v, o, do, lse, ctx.scale, ctx.causal)
+        if Dp != ctx.D:
+            dq, dk, dv = dq[..., :ctx.D], dk[..., :ctx.D], dv[..., :ctx.D]
+        return dq, dk, dv, None, None
+
+
+def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, scale: Optional[float] = None,
+              causal: bool = True) -> torch.Tensor:
+    """softmax(q k^T * scale + causal_mask) v with GQA head sharing; [B,S,H,D] layout, bf16."""
+    if scale is None:
+        scale = q.shape[-1] ** -0.5
+    return _AttentionFn.apply(q, k, v, float(scale), bool(causal))
