@@ -31,6 +31,7 @@ extern "C" {
 int b200_version(void);                 /* ABI version (monotonic integer) */
 const char* b200_last_error(void);      /* thread-local message of the last failing call */
 int b200_device_ok(void);               /* 1 if the current device is compute capability 10.x */
+unsigned long long b200_launch_count(void); /* kernels launched by this library so far (process-wide) */
 
 /* ---- dense contraction engine (tcgen05 + TMA) ----------------------------------------------
  * D[b] = alpha*alpha_vec[b] * op(A[b]) op(B[b]) + beta*beta_vec[b] * C[b],  b in [0,batch)
@@ -97,6 +98,14 @@ int b200_sumsq(const void* x, int x_is_bf16, float* out, long long numel, int ba
 /* hi = bf16((src + diag_add*I)*scale), lo = bf16(that - hi) (lo may be NULL); strided [rows,cols] */
 int b200_split_bf16(const float* src, long long ld_src, void* hi, void* lo, long long ld_dst,
                     int rows, int cols, float scale, float diag_add, void* stream);
+
+/* ---- Shampoo elementwise pieces (optimizers/shampoo.py:351-359, 365-373) ----------------------
+ * ema_split: m = beta*m + (1-beta)*g*gscale ; mhat = m*inv_bc -> out32 (f32), hi/lo (bf16 split) */
+int b200_ema_split(const void* g, int g_is_bf16, float* m, float* out32, void* hi, void* lo,
+                   long long n, float beta, float gscale, float inv_bc, void* stream);
+/* p[b] = p[b]*decay + coef[b]*pre[b] + coef_d[b]*d[b] ; p16 = bf16(p) (grafting + decoupled wd) */
+int b200_graft_update(float* p32, void* p16, const float* pre, const float* d, long long numel,
+                      int batch, const float* coef, const float* coef_d, float decay, void* stream);
 
 /* ---- RMSNorm (arch/llama.py:50-56) and RoPE (arch/llama_standard.py:74-75,117-127) ------------ */
 int b200_rmsnorm_fwd(const void* x, const void* w, void* y, float* rstd, int rows, int H,

@@ -20,6 +20,7 @@ SIGNATURES = {
     "b200_version": (_i, []),
     "b200_last_error": (C.c_char_p, []),
     "b200_device_ok": (_i, []),
+    "b200_launch_count": (C.c_ulonglong, []),
     "b200_gemm_bf16": (_i, [_i, _i, _i, _i, _i, _i, _vp, _ll, _ll, _vp, _ll, _ll, _vp, _ll, _ll,
                             _vp, _ll, _ll, _i, _f, _f, _vp, _vp, _i, _vp]),
     "b200_newton_schulz_workspace_bytes": (_sz, [_i, _i, _i, _i]),
@@ -33,6 +34,8 @@ SIGNATURES = {
     "b200_clip_accum": (_i, [_vp, _i, _vp, _ll, _f, _f, _i, _vp]),
     "b200_sumsq": (_i, [_vp, _i, _vp, _ll, _i, _i, _vp]),
     "b200_split_bf16": (_i, [_vp, _ll, _vp, _vp, _ll, _i, _i, _f, _f, _vp]),
+    "b200_ema_split": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _ll, _f, _f, _f, _vp]),
+    "b200_graft_update": (_i, [_vp, _vp, _vp, _vp, _ll, _i, _vp, _vp, _f, _vp]),
     "b200_rmsnorm_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _f, _i, _vp]),
     "b200_rmsnorm_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "b200_rope": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),

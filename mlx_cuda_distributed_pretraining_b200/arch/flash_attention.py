@@ -1,0 +1,75 @@
+"""FlashAttention module with the reference's constructor and call surface
+(arch/flash_attention.py:32-41,158-194), running the fused sm_100a kernels.
+
+The reference materialises softmax(QK^T*scale + mask)V un-tiled (:97-156); here the same result
+comes from `ops.attention` (tcgen05 forward + backward, online softmax, GQA head sharing).
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+from torch import nn
+
+from .. import ops
+
+
+class CausalMask:
+    """Marker for the additive causal mask the reference builds in arch/llama.py:384-387
+    (-inf strictly above the diagonal).  The fused kernel applies it implicitly."""
+
+    def __init__(self, seq_len: int):
+        self.seq_len = seq_len
+
+    def dense(self, dtype=torch.float32, device="cpu") -> torch.Tensor:
+        m = torch.full((self.seq_len, self.seq_len), float("-inf"), dtype=dtype, device=device)
+        return torch.triu(m, diagonal=1)[None, None]
+
+
+class FlashAttention(nn.Module):
+    def __init__(self, hidden_size: int, num_heads: int, num_kv_heads: Optional[int] = None,
+                 head_dim: Optional[int] = None, dropout: float = 0.0, use_bias: bool = False,
+                 flash_block_size: int = 128):
+        super().__init__()
+        self.hidden_size = hidden_size
+        self.num_heads = num_heads
+        self.num_kv_heads = num_kv_heads or num_heads
+        self.head_dim = head_dim or (hidden_size // num_heads)
+        if dropout != 0.0:
+            raise ValueError("attention dropout is not supported by the fused kernel (reference default 0.0)")
+        self.dropout = dropout
+        self.flash_block_size = flash_block_size  # accepted for config compatibility (kernel tiles are 128)
+        self.q_proj = nn.Linear(hidden_size, self.num_heads * self.head_dim, bias=use_bias)
+        self.k_proj = nn.Linear(hidden_size, self.num_kv_heads * self.head_dim, bias=use_bias)
+        self.v_proj = nn.Linear(hidden_size, self.num_kv_heads * self.head_dim, bias=use_bias)
+        self.o_proj = nn.Linear(self.num_heads * self.head_dim, hidden_size, bias=use_bias)
+        self.scale = self.head_dim ** -0.5
+        self.rope_tables = None  # (cos, sin) set by the parent when RoPE is enabled
+
+    def _flash_attention(self, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, mask=None) -> torch.Tensor:
+        """q [B,S,H,D], k/v [B,S,Hk,D] -> [B,S,H,D]."""
+        if mask is None:
+            causal = False
+        elif isinstance(mask, CausalMask):
+            causal = True
+        else:
+            raise NotImplementedError(
+                "the fused kernel supports mask=None or the causal mask (CausalMask); "
+                "arbitrary additive masks are outside the reference's training path")
+        dt = q.dtype
+        if dt != torch.bfloat16:  # tensor cores run bf16 operands with fp32 accumulation
+            q, k, v = q.to(torch.bfloat16), k.to(torch.bfloat16), v.to(torch.bfloat16)
+        o = ops.attention(q, k, v, self.scale, causal)
+        return o if dt == torch.bfloat16 else o.to(dt)
+
+    def forward(self, x: torch.Tensor, mask=None) -> torch.Tensor:
+        B, S, _ = x.shape
+        q = self.q_proj(x).reshape(B, S, self.num_heads, self.head_dim)
+        k = self.k_proj(x).reshape(B, S, self.num_kv_heads, self.head_dim)
+        v = self.v_proj(x).reshape(B, S, self.num_kv_heads, self.head_dim)
+        if self.rope_tables is not None:
+            cos_t, sin_t = self.rope_tables
+            q = ops.rope(q, cos_t[:S], sin_t[:S])
+            k = ops.rope(k, cos_t[:S], sin_t[:S])
+        ctx = self._flash_attention(q, k, v, mask)
+        return self.o_proj(ctx.reshape(B, S, self.num_heads * self.head_dim))

@@ -391,7 +391,7 @@ int launch_bwd(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap
   }
   dim3 grid((a.S + BT - 1) / BT, a.Hk, a.B);
   kern<<<grid, BWD_THREADS, Cfg::SMEM_BYTES, stream>>>(tmQ, tmK, tmV, tmDO, a);
-  B200_CHECK_CUDA(cudaGetLastError());
+  B200_CHECK_LAUNCH();
   return B200_OK;
 }
 
@@ -427,7 +427,7 @@ int attn_bwd(const void* q, const void* k, const void* v, const void* o, const v
       attn_delta_kernel<64><<<blocks, 256, 0, stream>>>((const __nv_bfloat16*)o, (const __nv_bfloat16*)d_o, delta, B, S, H);
     else
       attn_delta_kernel<128><<<blocks, 256, 0, stream>>>((const __nv_bfloat16*)o, (const __nv_bfloat16*)d_o, delta, B, S, H);
-    B200_CHECK_CUDA(cudaGetLastError());
+    B200_CHECK_LAUNCH();
   }
   CUtensorMap tmQ, tmK, tmV, tmDO;
   int rc;
@@ -454,7 +454,7 @@ int attn_bwd(const void* q, const void* k, const void* v, const void* o, const v
     long long blocks = (nvec + 255) / 256;
     if (blocks > (long long)num_sms() * 8) blocks = (long long)num_sms() * 8;
     f32_to_bf16_kernel<<<(int)blocks, 256, 0, stream>>>(dq_acc, reinterpret_cast<__nv_bfloat16*>(dq), nvec);
-    B200_CHECK_CUDA(cudaGetLastError());
+    B200_CHECK_LAUNCH();
   }
   return B200_OK;
 }

@@ -313,7 +313,7 @@ int launch_fwd(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap
   }
   dim3 grid((a.S + ATT_BQ - 1) / ATT_BQ, a.H, a.B);
   kern<<<grid, FWD_THREADS, Cfg::SMEM_BYTES, stream>>>(tmQ, tmK, tmV, a);
-  B200_CHECK_CUDA(cudaGetLastError());
+  B200_CHECK_LAUNCH();
   return B200_OK;
 }
 

@@ -34,6 +34,10 @@ int sumsq(const void* x, int x_is_bf16, float* out, long long numel, int batch, 
           cudaStream_t stream);
 int split_bf16(const float* src, long long ld_src, void* hi, void* lo, long long ld_dst, int rows,
                int cols, float scale, float diag_add, cudaStream_t stream);
+int ema_split(const void* g, int g_is_bf16, float* m, float* out32, void* hi, void* lo, long long n,
+              float beta, float gscale, float inv_bc, cudaStream_t stream);
+int graft_update(float* p32, void* p16, const float* pre, const float* d, long long numel, int batch,
+                 const float* coef, const float* coef_d, float decay, cudaStream_t stream);
 int rmsnorm_fwd(const void* x, const void* w, void* y, float* rstd, int rows, int H, float eps,
                 int is_bf16, cudaStream_t stream);
 int rmsnorm_bwd(const void* dy, const void* x, const void* w, const float* rstd, void* dx,
@@ -54,6 +58,8 @@ extern "C" {
 
 int b200_version(void) { return 1; }
 const char* b200_last_error(void) { return b200::last_error(); }
+
+unsigned long long b200_launch_count(void) { return b200::launch_count(); }
 
 int b200_device_ok(void) {
   int dev = 0, major = 0;
@@ -122,6 +128,14 @@ int b200_sumsq(const void* x, int x_is_bf16, float* out, long long numel, int ba
 int b200_split_bf16(const float* src, long long ld_src, void* hi, void* lo, long long ld_dst,
                     int rows, int cols, float scale, float diag_add, void* stream) {
   return b200::split_bf16(src, ld_src, hi, lo, ld_dst, rows, cols, scale, diag_add, S_(stream));
+}
+int b200_ema_split(const void* g, int g_is_bf16, float* m, float* out32, void* hi, void* lo,
+                   long long n, float beta, float gscale, float inv_bc, void* stream) {
+  return b200::ema_split(g, g_is_bf16, m, out32, hi, lo, n, beta, gscale, inv_bc, S_(stream));
+}
+int b200_graft_update(float* p32, void* p16, const float* pre, const float* d, long long numel,
+                      int batch, const float* coef, const float* coef_d, float decay, void* stream) {
+  return b200::graft_update(p32, p16, pre, d, numel, batch, coef, coef_d, decay, S_(stream));
 }
 int b200_rmsnorm_fwd(const void* x, const void* w, void* y, float* rstd, int rows, int H,
                      float eps, int is_bf16, void* stream) {

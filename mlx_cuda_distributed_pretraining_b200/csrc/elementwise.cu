@@ -19,9 +19,6 @@ namespace {
 
 constexpr int EW_THREADS = 256;
 
-template <typename T>
-struct Vec8;  // 8 elements per thread per iteration
-
 __device__ __forceinline__ void load8(const float* p, float* f) {
   const float4 a = *reinterpret_cast<const float4*>(p);
   const float4 b = *reinterpret_cast<const float4*>(p + 4);
@@ -301,6 +298,42 @@ split_bf16_kernel(const float* __restrict__ src, long long ld_src, __nv_bfloat16
   }
 }
 
+
+// Shampoo momentum (optimizers/shampoo.py:351-359): m = beta*m + (1-beta)*g ; mhat = m/bias_corr.
+// Emits mhat in fp32 (pass-through part of the update) and as a bf16 hi/lo pair (GEMM operands).
+template <typename G>
+__global__ void __launch_bounds__(EW_THREADS)
+ema_split_kernel(const G* __restrict__ g, float* __restrict__ m, float* __restrict__ out32,
+                 __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, long long n,
+                 float beta, float gscale, float inv_bc) {
+  for (long long i = (long long)blockIdx.x * EW_THREADS + threadIdx.x; i < n;
+       i += (long long)gridDim.x * EW_THREADS) {
+    const float mm = beta * m[i] + (1.0f - beta) * ldf(g + i) * gscale;
+    m[i] = mm;
+    const float mh = mm * inv_bc;
+    out32[i] = mh;
+    const __nv_bfloat16 h = __float2bfloat16_rn(mh);
+    hi[i] = h;
+    if (lo) lo[i] = __float2bfloat16_rn(mh - __bfloat162float(h));
+  }
+}
+
+// Grafted Shampoo update (optimizers/shampoo.py:365-373), batched over same-shape matrices:
+// p = p*decay + coef[b]*pre + coef_d[b]*d ; grid = (blocks, batch)
+__global__ void __launch_bounds__(EW_THREADS)
+graft_update_kernel(float* __restrict__ p32, __nv_bfloat16* __restrict__ p16,
+                    const float* __restrict__ pre, const float* __restrict__ d, long long numel,
+                    const float* __restrict__ coef, const float* __restrict__ coef_d, float decay) {
+  const long long base = (long long)blockIdx.y * numel;
+  const float c = coef[blockIdx.y], cd = coef_d[blockIdx.y];
+  for (long long i = (long long)blockIdx.x * EW_THREADS + threadIdx.x; i < numel;
+       i += (long long)gridDim.x * EW_THREADS) {
+    const float v = p32[base + i] * decay + c * pre[base + i] + cd * d[base + i];
+    p32[base + i] = v;
+    if (p16) p16[base + i] = __float2bfloat16_rn(v);
+  }
+}
+
 inline int ew_grid(long long n_per_thread_items) {
   long long blocks = (n_per_thread_items + EW_THREADS - 1) / EW_THREADS;
   const long long cap = (long long)num_sms() * 8;
@@ -333,7 +366,7 @@ int muon_momentum(const void* g, int g_is_bf16, float* buf, void* u_bf16, float*
   else
     muon_momentum_kernel<float><<<grid, EW_THREADS, 0, stream>>>(
         (const float*)g, buf, (__nv_bfloat16*)u_bf16, sumsq, numel, mu, nesterov, gscale);
-  B200_CHECK_CUDA(cudaGetLastError());
+  B200_CHECK_LAUNCH();
   return B200_OK;
 }
 
@@ -341,7 +374,7 @@ int ns_scales(const float* sumsq, float* inv_norm, float* inv_norm_sq, int batch
               cudaStream_t stream) {
   ns_scales_kernel<<<(batch + 127) / 128, 128, 0, stream>>>(sumsq, inv_norm, inv_norm_sq, batch,
                                                            eps);
-  B200_CHECK_CUDA(cudaGetLastError());
+  B200_CHECK_LAUNCH();
   return B200_OK;
 }
 
@@ -357,7 +390,7 @@ int axpy_update(float* p32, void* p16, const void* x, int x_is_bf16, long long n
   else
     axpy_update_kernel<float><<<grid, EW_THREADS, 0, stream>>>(p32, (__nv_bfloat16*)p16,
                                                               (const float*)x, n, s);
-  B200_CHECK_CUDA(cudaGetLastError());
+  B200_CHECK_LAUNCH();
   return B200_OK;
 }
 
@@ -371,7 +404,7 @@ int sgd_momentum(float* p32, void* p16, const void* g, int g_is_bf16, float* buf
   else
     sgd_momentum_kernel<float><<<grid, EW_THREADS, 0, stream>>>(
         p32, (__nv_bfloat16*)p16, (const float*)g, buf, n, mu, nesterov, lr, gscale);
-  B200_CHECK_CUDA(cudaGetLastError());
+  B200_CHECK_LAUNCH();
   return B200_OK;
 }
 
@@ -390,7 +423,7 @@ int adamw(float* p32, void* p16, const void* g, int g_is_bf16, float* m, float* 
     adamw_kernel<float><<<grid, EW_THREADS, 0, stream>>>(p32, (__nv_bfloat16*)p16, (const float*)g,
                                                         m, v, n, lr, b1, b2, eps, wd, bc1, bc2,
                                                         gscale);
-  B200_CHECK_CUDA(cudaGetLastError());
+  B200_CHECK_LAUNCH();
   return B200_OK;
 }
 
@@ -405,7 +438,7 @@ int adam_direction(float* d, const void* g, int g_is_bf16, float* m, float* v, l
   else
     adam_direction_kernel<float><<<grid, EW_THREADS, 0, stream>>>(d, (const float*)g, m, v, n, lr,
                                                                  b1, b2, eps, bc1, bc2, gscale);
-  B200_CHECK_CUDA(cudaGetLastError());
+  B200_CHECK_LAUNCH();
   return B200_OK;
 }
 
@@ -420,7 +453,7 @@ int clip_accum(const void* g, int g_is_bf16, float* acc, long long n, float clip
   else
     clip_accum_kernel<float><<<grid, EW_THREADS, 0, stream>>>((const float*)g, acc, n, clip, scale,
                                                              init);
-  B200_CHECK_CUDA(cudaGetLastError());
+  B200_CHECK_LAUNCH();
   return B200_OK;
 }
 
@@ -437,7 +470,7 @@ int sumsq(const void* x, int x_is_bf16, float* out, long long numel, int batch, 
     sumsq_kernel<__nv_bfloat16><<<grid, EW_THREADS, 0, stream>>>((const __nv_bfloat16*)x, out, numel);
   else
     sumsq_kernel<float><<<grid, EW_THREADS, 0, stream>>>((const float*)x, out, numel);
-  B200_CHECK_CUDA(cudaGetLastError());
+  B200_CHECK_LAUNCH();
   return B200_OK;
 }
 
@@ -448,7 +481,34 @@ int split_bf16(const float* src, long long ld_src, void* hi, void* lo, long long
   split_bf16_kernel<<<grid, EW_THREADS, 0, stream>>>(src, ld_src, (__nv_bfloat16*)hi,
                                                      (__nv_bfloat16*)lo, ld_dst, rows, cols, scale,
                                                      diag_add);
-  B200_CHECK_CUDA(cudaGetLastError());
+  B200_CHECK_LAUNCH();
+  return B200_OK;
+}
+
+int ema_split(const void* g, int g_is_bf16, float* m, float* out32, void* hi, void* lo, long long n,
+              float beta, float gscale, float inv_bc, cudaStream_t stream) {
+  B200_CHECK_ARG(n > 0, "ema_split: empty");
+  const int grid = ew_grid(n);
+  if (g_is_bf16)
+    ema_split_kernel<__nv_bfloat16><<<grid, EW_THREADS, 0, stream>>>(
+        (const __nv_bfloat16*)g, m, out32, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, n, beta, gscale, inv_bc);
+  else
+    ema_split_kernel<float><<<grid, EW_THREADS, 0, stream>>>(
+        (const float*)g, m, out32, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, n, beta, gscale, inv_bc);
+  B200_CHECK_LAUNCH();
+  return B200_OK;
+}
+
+int graft_update(float* p32, void* p16, const float* pre, const float* d, long long numel, int batch,
+                 const float* coef, const float* coef_d, float decay, cudaStream_t stream) {
+  B200_CHECK_ARG(numel > 0 && batch > 0, "graft_update: empty");
+  int gx = ew_grid(numel);
+  const int cap = (num_sms() * 8 + batch - 1) / batch;
+  if (gx > cap) gx = cap < 1 ? 1 : cap;
+  dim3 grid(gx, batch);
+  graft_update_kernel<<<grid, EW_THREADS, 0, stream>>>(p32, (__nv_bfloat16*)p16, pre, d, numel, coef,
+                                                       coef_d, decay);
+  B200_CHECK_LAUNCH();
   return B200_OK;
 }
 

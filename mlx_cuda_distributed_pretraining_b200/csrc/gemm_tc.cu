@@ -283,7 +283,7 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& 
   const int total = args.tiles_m * args.tiles_n * args.batch;
   const int grid = total < num_sms() ? total : num_sms();
   kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, args);
-  B200_CHECK_CUDA(cudaGetLastError());
+  B200_CHECK_LAUNCH();
   return B200_OK;
 }
 

@@ -4,6 +4,7 @@
 #include <stdarg.h>
 #include <stdio.h>
 
+#include <atomic>
 #include <mutex>
 
 namespace b200 {
@@ -80,6 +81,10 @@ int make_tensor_map(CUtensorMap* out, const void* base, CUtensorMapDataType dtyp
   }
   return B200_OK;
 }
+
+static std::atomic<unsigned long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+unsigned long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
 
 int num_sms() {
   static int n = 0;

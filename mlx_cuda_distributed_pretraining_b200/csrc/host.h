@@ -32,6 +32,16 @@ const char* last_error();
     }                                                                                      \
   } while (0)
 
+// every kernel launch of the library is counted (bench.py reports it as gpu_launches)
+void count_launch();
+unsigned long long launch_count();
+
+#define B200_CHECK_LAUNCH()                  \
+  do {                                       \
+    ::b200::count_launch();                  \
+    B200_CHECK_CUDA(cudaGetLastError());     \
+  } while (0)
+
 // Builds a tiled tensor map with 128B swizzle over a row-major array of `elem_bytes`-sized
 // elements. dims/strides are listed innermost-first; strides_bytes[i] is the byte stride of
 // dims[i+1] (rank-1 entries). Returns 0 on success.

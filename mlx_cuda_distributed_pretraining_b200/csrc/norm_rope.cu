@@ -183,7 +183,7 @@ int rmsnorm_fwd_t(const T* x, const T* w, T* y, float* rstd, int rows, int H, fl
     case 3: case 4: rmsnorm_fwd_kernel<T, 4><<<grid, RN_THREADS, 0, stream>>>(x, w, y, rstd, rows, H, eps); break;
     default: rmsnorm_fwd_kernel<T, RN_MAX_VEC><<<grid, RN_THREADS, 0, stream>>>(x, w, y, rstd, rows, H, eps); break;
   }
-  B200_CHECK_CUDA(cudaGetLastError());
+  B200_CHECK_LAUNCH();
   return B200_OK;
 }
 
@@ -198,7 +198,7 @@ int rmsnorm_bwd_t(const T* dy, const T* x, const T* w, const float* rstd, T* dx,
     case 3: case 4: rmsnorm_bwd_kernel<T, 4><<<grid, RN_THREADS, 0, stream>>>(dy, x, w, rstd, dx, dw, rows, H); break;
     default: rmsnorm_bwd_kernel<T, RN_MAX_VEC><<<grid, RN_THREADS, 0, stream>>>(dy, x, w, rstd, dx, dw, rows, H); break;
   }
-  B200_CHECK_CUDA(cudaGetLastError());
+  B200_CHECK_LAUNCH();
   return B200_OK;
 }
 
@@ -248,7 +248,7 @@ int rope(const void* x, void* y, const float* cos_t, const float* sin_t, int B, 
   else
     rope_kernel<float><<<(int)blocks, 256, 0, stream>>>((const float*)x, (float*)y, cos_t, sin_t,
                                                         nvec, S, NH, D, sign);
-  B200_CHECK_CUDA(cudaGetLastError());
+  B200_CHECK_LAUNCH();
   return B200_OK;
 }
 

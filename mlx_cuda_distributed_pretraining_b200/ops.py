@@ -21,6 +21,41 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+class KernelTimer:
+    """Optional CUDA-event bracketing of kernel families on the launching stream (bench.py's
+    live roofline measurement).  Disabled (None) in normal runs: zero overhead."""
+
+    def __init__(self):
+        self.events = {}
+
+    def start(self, name: str):
+        e0 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        return (name, e0)
+
+    def stop(self, tok) -> None:
+        name, e0 = tok
+        e1 = torch.cuda.Event(enable_timing=True)
+        e1.record()
+        self.events.setdefault(name, []).append((e0, e1))
+
+    def totals_ms(self):
+        torch.cuda.synchronize()
+        return {k: (sum(a.elapsed_time(b) for a, b in v), len(v)) for k, v in self.events.items()}
+
+
+TIMER: Optional[KernelTimer] = None
+
+
+def _t0(name: str):
+    return TIMER.start(name) if TIMER is not None else None
+
+
+def _t1(tok) -> None:
+    if tok is not None:
+        TIMER.stop(tok)
+
+
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
@@ -292,8 +327,10 @@ def attention_fwd_raw(q, k, v, scale: float, causal: bool):
     Hk = k.shape[2]
     o = torch.empty_like(q)
     lse = torch.empty((B, H, S), device=q.device, dtype=torch.float32)
+    tok = _t0("attn_fwd")
     check(lib().b200_attn_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), lse.data_ptr(),
                               B, S, H, Hk, D, float(scale), int(causal), _stream()), "b200_attn_fwd")
+    _t1(tok)
     return o, lse
 
 
@@ -305,10 +342,12 @@ def attention_bwd_raw(q, k, v, o, do, lse, scale: float, causal: bool):
     dv = torch.empty_like(v)
     nbytes = int(lib().b200_attn_bwd_workspace_bytes(B, S, H, Hk, D))
     ws = torch.empty(max(nbytes, 16), device=q.device, dtype=torch.uint8)
+    tok = _t0("attn_bwd")
     check(lib().b200_attn_bwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), do.data_ptr(),
                               lse.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), B, S, H,
                               Hk, D, float(scale), int(causal), ws.data_ptr(), ws.numel(), _stream()),
           "b200_attn_bwd")
+    _t1(tok)
     return dq, dk, dv
 
 
@@ -344,3 +383,40 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, scale: Optional
     if scale is None:
         scale = q.shape[-1] ** -0.5
     return _AttentionFn.apply(q, k, v, float(scale), bool(causal))
+
+
+# ------------------------------------------------------------------------------------------------
+# raw strided GEMM + Shampoo elementwise helpers
+# ------------------------------------------------------------------------------------------------
+def gemm_raw(a_mn: bool, b_mn: bool, M: int, N: int, K: int, batch: int,
+             A: torch.Tensor, lda: int, strideA: int, B: torch.Tensor, ldb: int, strideB: int,
+             C: Optional[torch.Tensor], ldc: int, strideC: int, D: torch.Tensor, ldd: int, strideD: int,
+             alpha: float = 1.0, beta: float = 0.0, alpha_vec: Optional[torch.Tensor] = None,
+             beta_vec: Optional[torch.Tensor] = None, force_bn: int = 0) -> None:
+    """Strided/batched GEMM on views (sub-blocks of larger matrices): explicit leading dims."""
+    if A.dtype != torch.bfloat16 or B.dtype != torch.bfloat16:
+        raise ValueError("gemm_raw: A and B must be bf16")
+    out_f32 = _is_bf16(D, "D") == 0
+    if C is not None and C.dtype != D.dtype:
+        raise ValueError("gemm_raw: C and D dtypes differ")
+    check(lib().b200_gemm_bf16(int(a_mn), int(b_mn), M, N, K, batch, A.data_ptr(), lda, strideA,
+                               B.data_ptr(), ldb, strideB, _ptr(C), ldc, strideC, D.data_ptr(), ldd,
+                               strideD, int(out_f32), float(alpha), float(beta), _ptr(alpha_vec),
+                               _ptr(beta_vec), int(force_bn), _stream()), "b200_gemm_bf16")
+
+
+def ema_split(g, m, out32, hi, lo, beta: float, gscale: float, inv_bc: float) -> None:
+    check(lib().b200_ema_split(g.data_ptr(), _is_bf16(g, "g"), m.data_ptr(), out32.data_ptr(),
+                               hi.data_ptr(), _ptr(lo), g.numel(), float(beta), float(gscale),
+                               float(inv_bc), _stream()), "b200_ema_split")
+
+
+def graft_update(p32, p16, pre, d, numel: int, batch: int, coef, coef_d, decay: float) -> None:
+    check(lib().b200_graft_update(p32.data_ptr(), _ptr(p16), pre.data_ptr(), d.data_ptr(), numel, batch,
+                                  coef.data_ptr(), coef_d.data_ptr(), float(decay), _stream()),
+          "b200_graft_update")
+
+
+def sumsq_raw(x: torch.Tensor, out: torch.Tensor, numel: int, batch: int, zero_first: bool = True) -> None:
+    check(lib().b200_sumsq(x.data_ptr(), _is_bf16(x, "x"), out.data_ptr(), numel, batch, int(zero_first),
+                           _stream()), "b200_sumsq")

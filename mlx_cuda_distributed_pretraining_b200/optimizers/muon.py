@@ -1,0 +1,140 @@
+"""Muon with the reference's surface (optimizers/muon.py:7-141), running on the sm_100a kernels.
+
+    opt = Muon(learning_rate=float|callable, momentum=0.95, nesterov=True, ns_steps=5,
+               alternate_optimizer=None, betas=None, eps=None, weight_decay=None)
+    opt.update(model, gradients)      # the one call the trainer makes (core/training.py:1690,1700)
+    opt.state[name]["momentum_buffer"], opt.count, opt.zeropower_via_newtonschulz5(G, steps)
+
+Semantics follow the reference's intended math with its wiring defects fixed:
+gradients are matched by flattened name and the update is applied to the model in place.
+Per 2-D shape group the step is: fused momentum+Nesterov+sum-of-squares pass -> batched
+Newton-Schulz on tcgen05 -> fused `p += -lr*max(1,r/c)^0.5 * X` pass (fp32 master + bf16 shadow).
+Non-2-D parameters go to `alternate_optimizer` if given, else to the SGD-momentum fallback
+(muon.py:119-138).  `betas/eps/weight_decay` are accepted and ignored, as in the reference (:41-52).
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict, Optional, Tuple, Union
+
+import torch
+
+from .. import ops
+from ..flat import ParamStore, get_store
+
+
+class Muon:
+    def __init__(self, learning_rate: Union[float, Callable] = 0.02, momentum: float = 0.95,
+                 nesterov: bool = True, ns_steps: int = 5, alternate_optimizer=None,
+                 betas: Optional[Tuple[float, float]] = None, eps: Optional[float] = None,
+                 weight_decay: Optional[float] = None):
+        self._learning_rate = learning_rate
+        self.momentum = momentum
+        self.nesterov = nesterov
+        self.ns_steps = ns_steps
+        self.alternate_optimizer = alternate_optimizer
+        self.state: Dict[str, Dict[str, torch.Tensor]] = {}
+        self.count = 0
+        self.grad_scale = 1.0        # e.g. 1/world_size for the data-parallel mean
+        self.use_accumulated = False  # read gradients from store.acc (fp32) instead of store.grad
+        self._store: Optional[ParamStore] = None
+        self._buf = None
+
+    # -- reference surface ---------------------------------------------------------------------
+    @property
+    def learning_rate(self) -> float:
+        return self._lr(self.count)
+
+    def _lr(self, count: int) -> float:
+        lr = self._learning_rate(count) if callable(self._learning_rate) else self._learning_rate
+        return float(lr)
+
+    def zeropower_via_newtonschulz5(self, G: torch.Tensor, steps: int) -> torch.Tensor:
+        return ops.zeropower_via_newtonschulz5(G, steps)
+
+    # -- state -----------------------------------------------------------------------------------
+    def init(self, model) -> None:
+        store = get_store(model)
+        if self._store is store:
+            return
+        self._store = store
+        dev = store.device
+        self._buf = torch.zeros(store.total, dtype=torch.float32, device=dev)  # momentum buffers
+        max_numel = max((g.numel for g in store.mat_groups), default=0)
+        max_batch = max((g.batch for g in store.mat_groups), default=1)
+        ws_bytes = max((ops.ns_workspace_bytes(g.batch, g.rows, g.cols, self.ns_steps)
+                        for g in store.mat_groups), default=0)
+        self._u = torch.empty(max(max_numel, 8), dtype=torch.bfloat16, device=dev)
+        self._x = torch.empty(max(max_numel, 8), dtype=torch.bfloat16, device=dev)
+        self._ws = torch.empty(max(ws_bytes, 256), dtype=torch.uint8, device=dev)
+        self._ss = torch.empty(max_batch, dtype=torch.float32, device=dev)
+        self._inv = torch.empty(max_batch, dtype=torch.float32, device=dev)
+        self._inv2 = torch.empty(max_batch, dtype=torch.float32, device=dev)
+        self.state = {}
+        for g in store.mat_groups:
+            for n in g.names:
+                self.state[n] = {"momentum_buffer": store.view(self._buf, n)}
+        if self.alternate_optimizer is None:
+            for e in store.vec_entries:
+                self.state[e.name] = {"momentum_buffer": store.view(self._buf, e.name)}
+        else:
+            self.alternate_optimizer.init_range(store, store.vec_offset, store.vec_end)
+
+    # -- step --------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def update(self, model, gradients=None) -> None:
+        self.init(model)
+        store = self._store
+        if gradients is not None:
+            store.load_gradients(gradients)
+        gsrc = store.acc if self.use_accumulated else store.grad
+        lr = self._lr(self.count)
+        lib = ops.lib()
+        stream = ops._stream()
+        a, b, c = ops.NS_COEFFS
+        for g in store.mat_groups:
+            n = g.numel
+            gg = gsrc[g.offset:g.offset + n]
+            buf = self._buf[g.offset:g.offset + n]
+            u = self._u[:n]
+            x = self._x[:n]
+            ops.check(lib.b200_muon_momentum(gg.data_ptr(), ops._is_bf16(gg, "grad"), buf.data_ptr(),
+                                             u.data_ptr(), self._ss.data_ptr(), g.rows * g.cols, g.batch,
+                                             float(self.momentum), int(self.nesterov),
+                                             float(self.grad_scale), stream), "b200_muon_momentum")
+            ops.check(lib.b200_ns_scales(self._ss.data_ptr(), self._inv.data_ptr(), self._inv2.data_ptr(),
+                                         g.batch, ops.NS_EPS, stream), "b200_ns_scales")
+            tok = ops._t0("newton_schulz")
+            ops.check(lib.b200_newton_schulz(u.data_ptr(), x.data_ptr(), g.batch, g.rows, g.cols,
+                                             self.ns_steps, a, b, c, self._inv.data_ptr(),
+                                             self._inv2.data_ptr(), self._ws.data_ptr(), self._ws.numel(),
+                                             stream), "b200_newton_schulz")
+            ops._t1(tok)
+            scaling = max(1.0, g.rows / g.cols) ** 0.5
+            p32 = store.master[g.offset:g.offset + n]
+            p16 = store.shadow[g.offset:g.offset + n] if store.mixed else None
+            ops.check(lib.b200_axpy_update(p32.data_ptr(), ops._ptr(p16), x.data_ptr(), 1, n,
+                                           float(-lr * scaling), stream), "b200_axpy_update")
+        if store.vec_end > store.vec_offset:
+            lo, hi = store.vec_offset, store.vec_end
+            if self.alternate_optimizer is not None:
+                self.alternate_optimizer.update_range(store, lo, hi, gsrc, self.grad_scale)
+            else:
+                p16 = store.shadow[lo:hi] if store.mixed else None
+                ops.sgd_momentum(store.master[lo:hi], p16, gsrc[lo:hi], self._buf[lo:hi], self.momentum,
+                                 self.nesterov, lr, self.grad_scale)
+        self.count += 1
+
+    # MLX-style aliases kept so callers written against mlx.optimizers.Optimizer keep working
+    def apply_gradients(self, gradients, model):
+        self.update(model, gradients)
+        return model
+
+    def step(self, model) -> None:
+        """torch-style: consume the gradients autograd left in the flat store."""
+        self.update(model, None)
+
+    def state_dict(self) -> Dict[str, torch.Tensor]:
+        out = {f"{n}.momentum_buffer": s["momentum_buffer"] for n, s in self.state.items()}
+        if self.alternate_optimizer is not None:
+            out.update(self.alternate_optimizer.state_dict())
+        return out

@@ -1,0 +1,162 @@
+"""CPU: the C-ABI library's symbol table, host-side logic (config, schedules, flat store, optimizer
+factory, DP helpers) and the rule that the product never imports the oracle."""
+import ctypes
+import re
+from pathlib import Path
+
+import pytest
+import torch
+import yaml
+
+ROOT = Path(__file__).resolve().parents[1]
+PKG = ROOT / "mlx_cuda_distributed_pretraining_b200"
+
+
+def test_capi_exports_every_declared_symbol(lib_built):
+    header = (ROOT / "include" / "b200_hotpath.h").read_text()
+    declared = set(re.findall(r"\b(b200_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 20
+    handle = ctypes.CDLL(str(lib_built))
+    missing = [s for s in sorted(declared) if not hasattr(handle, s)]
+    assert not missing, f"declared in include/b200_hotpath.h but not exported: {missing}"
+    from mlx_cuda_distributed_pretraining_b200._lib import SIGNATURES
+    assert set(SIGNATURES) == declared, set(SIGNATURES) ^ declared
+    handle.b200_version.restype = ctypes.c_int
+    assert handle.b200_version() >= 1
+    handle.b200_newton_schulz_workspace_bytes.restype = ctypes.c_size_t
+    # pure host arithmetic (no GPU): A,B [m,m] bf16 x2 + X_tmp
+    n = handle.b200_newton_schulz_workspace_bytes(2, 128, 256, 5)
+    assert n == 2 * 2 * 128 * 128 * 2 + 2 * 128 * 256 * 2
+
+
+def test_product_never_imports_oracle():
+    offenders = []
+    for p in list(PKG.rglob("*.py")) + [ROOT / "core" / "training.py"] + list((ROOT / "optimizers").glob("*.py")):
+        txt = p.read_text()
+        if re.search(r"^\s*(from|import)\s+oracle\b", txt, re.M):
+            offenders.append(str(p))
+    assert not offenders, offenders
+
+
+def test_no_cpu_fallback_without_device():
+    from mlx_cuda_distributed_pretraining_b200 import _lib, ops
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(_lib.B200Error):
+        ops.zeropower_via_newtonschulz5(torch.randn(8, 16))
+    with pytest.raises(_lib.B200Error):
+        ops.gemm(torch.zeros(8, 8, dtype=torch.bfloat16), torch.zeros(8, 8, dtype=torch.bfloat16))
+
+
+def test_configs_parse_and_match_baseline_dims():
+    from mlx_cuda_distributed_pretraining_b200.core.training import Config
+    want = {
+        "c1-llama2m-adamw.yaml": (128, 256, 4, 8, 8, 16, "adamw"),
+        "c2-llama80m-muon.yaml": (1024, 2816, 12, 16, 8, 64, "muon"),
+        "c3-llama400m-muon-dp8.yaml": (1024, 4096, 16, 16, 8, 64, "muon"),
+        "c4-llama256m-shampoo-dp4.yaml": (1024, 2816, 16, 16, 16, 64, "shampoo"),
+        "c5-llama1b-adamw-dp8.yaml": (2048, 5632, 16, 16, 16, 128, "adamw"),
+    }
+    for fn, (h, i, L, H, Hk, D, opt) in want.items():
+        c = Config.from_yaml(str(ROOT / "configs" / fn))
+        m = c.model
+        assert (m.dimensions["hidden_size"], m.dimensions["intermediate_size"], m.dimensions["num_layers"],
+                m.attention["num_heads"], m.attention["num_kv_heads"], m.attention["head_dim"]) == (h, i, L, H, Hk, D)
+        assert c.training.optimization["optimizer"] == opt
+    with pytest.raises(ValueError):
+        Config.from_dict({"data": {}, "model": {}, "training": {}, "logging": {}, "system": {}})
+    bad = yaml.safe_load((ROOT / "configs" / "c1-llama2m-adamw.yaml").read_text())
+    bad["system"]["no_such_key"] = 1
+    with pytest.raises(TypeError):  # unknown keys raise, as the reference's dataclasses do
+        Config.from_dict(bad)
+
+
+def test_schedules_equal_oracle():
+    from oracle import reference_math as R
+    from mlx_cuda_distributed_pretraining_b200.core.training import OptimizationManager, TrainingConfig
+    tc = TrainingConfig(hyperparameters={"learning_rate": 3e-4, "batch_size": 1},
+                        scheduler={"type": "cosine_with_warmup", "warmup_steps": 20, "min_lr_ratio": 0.1},
+                        optimization={"optimizer": "muon"})
+    s = OptimizationManager(tc, 200).create_scheduler()
+    r = R.make_schedule(tc.scheduler, 3e-4, 200)
+    for step in (0, 1, 19, 20, 21, 100, 219, 220, 1000):
+        assert s(step) == pytest.approx(r(step), rel=1e-12, abs=1e-18)
+
+
+def test_optimizer_factory_dispatch():
+    from mlx_cuda_distributed_pretraining_b200.core.training import OptimizationManager, TrainingConfig
+    from mlx_cuda_distributed_pretraining_b200.optimizers import AdamW, HybridOptimizer, Muon, Shampoo
+    def mk(opt):
+        tc = TrainingConfig(hyperparameters={"learning_rate": 1e-3, "batch_size": 1, "weight_decay": 0.1},
+                            scheduler={"type": "cosine", "min_lr_ratio": 0.1}, optimization=opt)
+        om = OptimizationManager(tc, 10)
+        return om.create_optimizer(om.create_scheduler())
+    assert isinstance(mk({"optimizer": "muon"}), Muon)
+    a = mk({"optimizer": "adamw", "betas": [0.9, 0.95], "eps": 1e-8})
+    assert isinstance(a, AdamW) and a.betas == (0.9, 0.95) and a.weight_decay == 0.1
+    s = mk({"optimizer": "shampoo"})
+    assert isinstance(s, Shampoo) and s.params.update_period == 100 and s.params.beta2 == 0.95
+    h = mk({"optimizer": "hybrid"})
+    assert isinstance(h, HybridOptimizer) and h.matrix_optimizer.alternate_optimizer is h.non_matrix_optimizer
+    with pytest.raises(ValueError):
+        mk({"optimizer": "lbfgs"})
+
+
+def test_param_store_layout_and_views():
+    from mlx_cuda_distributed_pretraining_b200.arch.llama import Model, ModelArgs
+    from mlx_cuda_distributed_pretraining_b200.flat import ParamStore, flatten_tree
+    from oracle import reference_math as R
+    args = ModelArgs(model_type="llama", hidden_size=64, num_hidden_layers=2, intermediate_size=96,
+                     num_attention_heads=4, head_dim=16, vocab_size=67, num_key_value_heads=2,
+                     tie_word_embeddings=True)
+    model = Model(args)
+    names = [n for n, _ in model.named_parameters()]
+    assert names == list(R.param_shapes(R.LlamaDims(64, 96, 2, 4, 2, 16, 67)))  # reference's flattened names
+    before = {n: p.detach().clone() for n, p in model.named_parameters()}
+    store = ParamStore(model, torch.bfloat16, torch.device("cpu"))
+    # same-shape matrices are contiguous batches; every group is 16-byte aligned
+    shapes = {(g.rows, g.cols): g.batch for g in store.mat_groups}
+    assert shapes[(64, 64)] == 4 and shapes[(32, 64)] == 4 and shapes[(96, 64)] == 4 and shapes[(64, 96)] == 2
+    assert all(g.offset % 128 == 0 for g in store.mat_groups)
+    for n, p in model.named_parameters():
+        assert p.dtype == torch.bfloat16 and p.grad is not None
+        assert torch.equal(store.view(store.master, n), before[n])
+        assert p.data_ptr() == store.view(store.shadow, n).data_ptr()
+        assert p.grad.data_ptr() == store.view(store.grad, n).data_ptr()
+    # explicit (nested) gradient dicts, as the reference trainer passes them
+    nested = {"layers": [{"mlp": {"gate_proj": {"weight": torch.ones(96, 64)}}}]}
+    flat = flatten_tree(nested)
+    assert list(flat) == ["layers.0.mlp.gate_proj.weight"]
+    store.load_gradients(nested)
+    assert float(store.view(store.grad, "layers.0.mlp.gate_proj.weight").float().sum()) == 96 * 64
+    with pytest.raises(KeyError):
+        store.load_gradients({"nope": torch.zeros(1)})
+
+
+def test_dp_helpers():
+    from mlx_cuda_distributed_pretraining_b200.distributed import dp
+    b = torch.arange(10).reshape(10, 1)
+    shards = [dp.shard_batch(b, r, 3) for r in range(3)]
+    assert [s.shape[0] for s in shards] == [3, 3, 4]          # last shard takes the remainder
+    assert torch.equal(torch.cat(shards), b)
+    owner = dp.partition_by_cost([5, 1, 1, 1, 4, 4], 2)
+    load = [sum(c for c, o in zip([5, 1, 1, 1, 4, 4], owner) if o == r) for r in range(2)]
+    assert abs(load[0] - load[1]) <= 1
+
+
+def test_synthetic_data_matches_oracle_stream():
+    from oracle import reference_math as R
+    from mlx_cuda_distributed_pretraining_b200.core.training import SyntheticData
+    d = SyntheticData(256, 4, 32, rank=1)
+    assert torch.equal(d.generate_batch(7), R.synthetic_batch(7, 1, 4, 32, 256))
+
+
+def test_tokenizer_byte_level_ids():
+    from mlx_cuda_distributed_pretraining_b200.core.training import DataConfig, TokenizerManager
+    cfg = DataConfig(input_file="synthetic", preprocessing={"max_context_size": 8},
+                     tokenizer={"normal_vocab_size": 256, "special_tokens": {"pad": "<pad>", "bos": "<bos>", "eos": "<eos>"}})
+    tk = TokenizerManager(cfg)
+    assert (tk.PAD_TOKEN, tk.BOS_TOKEN, tk.EOS_TOKEN, tk.VOCAB_SIZE) == (256, 257, 258, 259)
+    ids = tk.tokenize_doc("hello world, long")
+    assert ids[0] == 257 and ids[-1] == 258 and len(ids) == 10
+    assert tk.detokenize(ids[1:-1]) == "hello wo"

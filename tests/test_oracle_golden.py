@@ -1,0 +1,129 @@
+"""CPU: the oracle (oracle/reference_math.py) against golden vectors produced by running the
+reference's own Python over the NumPy mlx shim (tests/golden/make_golden.py).  fp32 both sides, so
+tolerances are fp32 round-off (different summation order only)."""
+import numpy as np
+import torch
+
+from oracle import reference_math as R
+
+RTOL = 2e-5
+
+
+def rel(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-30)
+
+
+def t(x):
+    return torch.from_numpy(np.asarray(x))
+
+
+def test_newton_schulz_matches_reference(golden):
+    for tag in ("wide", "tall", "square", "batched"):
+        x = R.newton_schulz5(t(golden[f"ns_{tag}_in"]), 5)
+        assert rel(x.numpy(), golden[f"ns_{tag}_out"]) < 5e-5, tag
+
+
+def test_muon_update_matches_reference(golden):
+    shapes = ("w_wide", "w_tall", "gain")
+    params = {k: t(golden[f"muon_param_{k}"]).clone() for k in shapes}
+    opt = R.MuonOracle(lambda step: 0.01 * (step + 1), momentum=0.95, nesterov=True, ns_steps=5)
+    for step in range(2):
+        grads = {k: t(golden[f"muon_s{step}_grad_{k}"]) for k in shapes}
+        upd = opt.update(params, grads)
+        for k in shapes:
+            assert rel(upd[k].numpy(), golden[f"muon_s{step}_upd_{k}"]) < 5e-5, (step, k)
+            assert rel(opt.state[k]["momentum_buffer"].numpy(), golden[f"muon_s{step}_buf_{k}"]) < 1e-6, (step, k)
+
+
+def test_inverse_pth_root_matches_reference(golden):
+    m = t(golden["root_in"])
+    assert rel(R.matrix_inverse_pth_root(m, 0.75).numpy(), golden["root_out_p075"]) < RTOL
+    assert rel(R.matrix_inverse_pth_root(m, 0.5).numpy(), golden["root_out_p05"]) < RTOL
+
+
+def test_shampoo_statistics_preconditioning_grafting(golden):
+    g1, g2 = t(golden["sh_g1"]), t(golden["sh_g2"])
+    cap, b2 = 32, 0.95
+    L = torch.zeros(cap, cap)
+    Rm = torch.zeros(40 if 40 < cap else cap, 40 if 40 < cap else cap)
+    for g in (g1, g2):
+        lg = g[:cap, :cap]
+        L = b2 * L + (1 - b2) * lg @ lg.T
+        Rm = b2 * Rm + (1 - b2) * lg.T @ lg
+    assert rel(L.numpy(), golden["sh_stat0"]) < RTOL
+    assert rel(Rm.numpy(), golden["sh_stat1"]) < RTOL
+    PL, PR = R.matrix_inverse_pth_root(L, 0.75), R.matrix_inverse_pth_root(Rm, 0.75)
+    assert rel(PL.numpy(), golden["sh_pre0"]) < 1e-4
+    assert rel(PR.numpy(), golden["sh_pre1"]) < 1e-4
+    pre = g2.clone()
+    pre[:cap, :cap] = PL @ g2[:cap, :cap] @ PR
+    assert rel(pre.numpy(), golden["sh_preconditioned"]) < 1e-4
+    gu, su = t(golden["graft_in_graft"]), t(golden["graft_in_shampoo"])
+    assert rel((su * (gu.norm() / su.norm())).numpy(), golden["graft_out"]) < RTOL
+
+
+def test_attention_matches_reference(golden):
+    S = 16
+    mask = R.causal_mask(S)
+    for tag in ("mha", "mqa", "gqa"):
+        q, k, v = (t(golden[f"attn_{tag}_{n}"]) for n in "qkv")
+        scale = 32 ** -0.5
+        assert rel(R.attention(q, k, v, scale, mask).numpy(), golden[f"attn_{tag}_causal"]) < RTOL, tag
+        assert rel(R.attention(q, k, v, scale, None).numpy(), golden[f"attn_{tag}_nomask"]) < RTOL, tag
+        # FlashAttention.__call__: projections + attention + o_proj
+        x = t(golden[f"attn_{tag}_x"])
+        lin = torch.nn.functional.linear
+        H = 4
+        Hk = k.shape[2]
+        qq = lin(x, t(golden[f"attn_{tag}_q_proj"])).reshape(2, S, H, 32)
+        kk = lin(x, t(golden[f"attn_{tag}_k_proj"])).reshape(2, S, Hk, 32)
+        vv = lin(x, t(golden[f"attn_{tag}_v_proj"])).reshape(2, S, Hk, 32)
+        y = lin(R.attention(qq, kk, vv, scale, mask).reshape(2, S, H * 32), t(golden[f"attn_{tag}_o_proj"]))
+        assert rel(y.numpy(), golden[f"attn_{tag}_call"]) < RTOL, tag
+
+
+def test_rmsnorm_mlp_match_reference(golden):
+    y = R.rmsnorm(t(golden["rms_x"]), t(golden["rms_w"]), 1e-5)
+    assert rel(y.numpy(), golden["rms_y"]) < RTOL
+    y = R.mlp(t(golden["mlp_x"]), t(golden["mlp_gate_proj"]), t(golden["mlp_up_proj"]), t(golden["mlp_down_proj"]))
+    assert rel(y.numpy(), golden["mlp_y"]) < RTOL
+
+
+def _model_params(golden):
+    # mlx tree_flatten names -> oracle names (identical by construction)
+    return {k.split("::", 1)[1]: t(golden[k]) for k in golden.files if k.startswith("model_param::")}
+
+
+def test_llama_forward_matches_reference(golden):
+    params = _model_params(golden)
+    d = R.LlamaDims(64, 96, 2, 4, 2, 16, 67)
+    assert set(R.param_shapes(d)) == set(params), "flattened parameter names differ from the reference's"
+    for name, shape in R.param_shapes(d).items():
+        assert tuple(params[name].shape) == shape, name
+    logits = R.llama_forward(params, t(golden["model_tokens"]), d)
+    assert rel(logits.numpy(), golden["model_logits"]) < 5e-5
+
+
+def test_schedule_matches_reference(golden):
+    sched = R.make_schedule({"type": "cosine_with_warmup", "warmup_steps": 10, "min_lr_ratio": 0.1}, 3e-4, 100)
+    got = np.array([sched(int(s)) for s in golden["sched_steps"]])
+    np.testing.assert_allclose(got, golden["sched_values"], rtol=1e-6, atol=1e-12)
+
+
+def test_newton_schulz_properties():
+    """Self-authored known-answer properties: singular values of NS5 output for
+    full-rank Gaussian wide matrices fall in [0.68, 1.14]; tall == transpose of wide."""
+    g = torch.Generator().manual_seed(0)
+    for shape in ((256, 512), (512, 128)):
+        G = torch.randn(shape, generator=g)
+        X = R.newton_schulz5(G)
+        sv = torch.linalg.svdvals(X)
+        assert 0.66 < sv.min() and sv.max() < 1.16, (shape, sv.min(), sv.max())
+        assert rel(R.newton_schulz5(G.T).numpy(), X.T.numpy()) < 1e-5
+
+
+def test_dp_contract():
+    g = [{"w": torch.ones(2, 2) * i} for i in (1.0, 3.0)]
+    assert torch.equal(R.mean_gradients(g)["w"], torch.ones(2, 2) * 2.0)
+    assert abs(R.token_weighted_loss([1.0, 3.0], [10, 30]) - 2.5) < 1e-12
