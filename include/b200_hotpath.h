@@ -100,9 +100,11 @@ int b200_split_bf16(const float* src, long long ld_src, void* hi, void* lo, long
                     int rows, int cols, float scale, float diag_add, void* stream);
 
 /* ---- Shampoo elementwise pieces (optimizers/shampoo.py:351-359, 365-373) ----------------------
- * ema_split: m = beta*m + (1-beta)*g*gscale ; mhat = m*inv_bc -> out32 (f32), hi/lo (bf16 split) */
+ * ema_split: m = beta*m + (1-beta)*g*gscale ; mhat = m*inv_bc -> out32 = out_scale*mhat (f32),
+ * hi/lo = bf16 split of mhat */
 int b200_ema_split(const void* g, int g_is_bf16, float* m, float* out32, void* hi, void* lo,
-                   long long n, float beta, float gscale, float inv_bc, void* stream);
+                   long long n, float beta, float gscale, float inv_bc, float out_scale,
+                   void* stream);
 /* p[b] = p[b]*decay + coef[b]*pre[b] + coef_d[b]*d[b] ; p16 = bf16(p) (grafting + decoupled wd) */
 int b200_graft_update(float* p32, void* p16, const float* pre, const float* d, long long numel,
                       int batch, const float* coef, const float* coef_d, float decay, void* stream);
@@ -110,8 +112,10 @@ int b200_graft_update(float* p32, void* p16, const float* pre, const float* d, l
 /* ---- RMSNorm (arch/llama.py:50-56) and RoPE (arch/llama_standard.py:74-75,117-127) ------------ */
 int b200_rmsnorm_fwd(const void* x, const void* w, void* y, float* rstd, int rows, int H,
                      float eps, int is_bf16, void* stream);
+size_t b200_rmsnorm_bwd_workspace_bytes(int rows, int H);   /* per-CTA dW partials */
 int b200_rmsnorm_bwd(const void* dy, const void* x, const void* w, const float* rstd, void* dx,
-                     float* dw_f32, int rows, int H, int is_bf16, void* stream);
+                     float* dw_f32, int rows, int H, int is_bf16, void* workspace,
+                     size_t workspace_bytes, void* stream);
 /* x,y: [B,S,NH,D]; cos_t,sin_t: f32 [S,D/2]; backward=1 applies the inverse rotation */
 int b200_rope(const void* x, void* y, const float* cos_t, const float* sin_t, int B, int S, int NH,
               int D, int backward, int is_bf16, void* stream);

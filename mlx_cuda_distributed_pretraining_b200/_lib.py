@@ -34,10 +34,11 @@ SIGNATURES = {
     "b200_clip_accum": (_i, [_vp, _i, _vp, _ll, _f, _f, _i, _vp]),
     "b200_sumsq": (_i, [_vp, _i, _vp, _ll, _i, _i, _vp]),
     "b200_split_bf16": (_i, [_vp, _ll, _vp, _vp, _ll, _i, _i, _f, _f, _vp]),
-    "b200_ema_split": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _ll, _f, _f, _f, _vp]),
+    "b200_ema_split": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _ll, _f, _f, _f, _f, _vp]),
     "b200_graft_update": (_i, [_vp, _vp, _vp, _vp, _ll, _i, _vp, _vp, _f, _vp]),
     "b200_rmsnorm_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _f, _i, _vp]),
-    "b200_rmsnorm_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "b200_rmsnorm_bwd_workspace_bytes": (_sz, [_i, _i]),
+    "b200_rmsnorm_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _sz, _vp]),
     "b200_rope": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "b200_attn_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _i, _vp]),
     "b200_attn_bwd_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),

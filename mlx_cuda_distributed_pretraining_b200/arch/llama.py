@@ -131,6 +131,7 @@ class Model(nn.Module):
         self.layers = nn.ModuleList([TransformerBlock(args) for _ in range(args.num_hidden_layers)])
         self.norm = RMSNorm(args.hidden_size, eps=args.rms_norm_eps)
         self.logit_scale = args.logit_scale
+        self._tied_w = None  # padded alias of the embedding for the logits GEMM (set lazily)
         self.lm_head = None if args.tie_word_embeddings else nn.Linear(args.hidden_size, args.vocab_size, bias=False)
 
     def forward(self, inputs: torch.Tensor, position_ids=None, attention_mask=None) -> torch.Tensor:
@@ -140,7 +141,18 @@ class Model(nn.Module):
         for layer in self.layers:
             h = layer(h, mask=mask, position_ids=position_ids)
         h = self.norm(h)
-        logits = torch.nn.functional.linear(h, self.embed_tokens.weight) if self.lm_head is None else self.lm_head(h)
+        if self.lm_head is None:
+            store = getattr(self, "_b200_store", None)
+            if store is not None and self._tied_w is None:
+                self._tied_w = store.tied_logits_weight() if store.tied_logits_weight() is not None else False
+            if self._tied_w is not None and self._tied_w is not False:
+                # V = 32003 is not a multiple of 8: run the GEMM on the zero-row-padded alias of E
+                # (aligned N), then drop the padded classes.  Same values, same gradients.
+                logits = torch.nn.functional.linear(h, self._tied_w)[..., :self.vocab_size]
+            else:
+                logits = torch.nn.functional.linear(h, self.embed_tokens.weight)
+        else:
+            logits = self.lm_head(h)
         if self.logit_scale is not None:
             logits = logits * self.logit_scale
         return logits

@@ -35,13 +35,15 @@ int sumsq(const void* x, int x_is_bf16, float* out, long long numel, int batch, 
 int split_bf16(const float* src, long long ld_src, void* hi, void* lo, long long ld_dst, int rows,
                int cols, float scale, float diag_add, cudaStream_t stream);
 int ema_split(const void* g, int g_is_bf16, float* m, float* out32, void* hi, void* lo, long long n,
-              float beta, float gscale, float inv_bc, cudaStream_t stream);
+              float beta, float gscale, float inv_bc, float out_scale, cudaStream_t stream);
 int graft_update(float* p32, void* p16, const float* pre, const float* d, long long numel, int batch,
                  const float* coef, const float* coef_d, float decay, cudaStream_t stream);
 int rmsnorm_fwd(const void* x, const void* w, void* y, float* rstd, int rows, int H, float eps,
                 int is_bf16, cudaStream_t stream);
+size_t rmsnorm_bwd_workspace_bytes(int rows, int H);
 int rmsnorm_bwd(const void* dy, const void* x, const void* w, const float* rstd, void* dx,
-                float* dw, int rows, int H, int is_bf16, cudaStream_t stream);
+                float* dw, int rows, int H, int is_bf16, void* ws, size_t ws_bytes,
+                cudaStream_t stream);
 int rope(const void* x, void* y, const float* cos_t, const float* sin_t, int B, int S, int NH,
          int D, int backward, int is_bf16, cudaStream_t stream);
 int attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int B, int S, int H,
@@ -130,8 +132,10 @@ int b200_split_bf16(const float* src, long long ld_src, void* hi, void* lo, long
   return b200::split_bf16(src, ld_src, hi, lo, ld_dst, rows, cols, scale, diag_add, S_(stream));
 }
 int b200_ema_split(const void* g, int g_is_bf16, float* m, float* out32, void* hi, void* lo,
-                   long long n, float beta, float gscale, float inv_bc, void* stream) {
-  return b200::ema_split(g, g_is_bf16, m, out32, hi, lo, n, beta, gscale, inv_bc, S_(stream));
+                   long long n, float beta, float gscale, float inv_bc, float out_scale,
+                   void* stream) {
+  return b200::ema_split(g, g_is_bf16, m, out32, hi, lo, n, beta, gscale, inv_bc, out_scale,
+                         S_(stream));
 }
 int b200_graft_update(float* p32, void* p16, const float* pre, const float* d, long long numel,
                       int batch, const float* coef, const float* coef_d, float decay, void* stream) {
@@ -141,9 +145,14 @@ int b200_rmsnorm_fwd(const void* x, const void* w, void* y, float* rstd, int row
                      float eps, int is_bf16, void* stream) {
   return b200::rmsnorm_fwd(x, w, y, rstd, rows, H, eps, is_bf16, S_(stream));
 }
+size_t b200_rmsnorm_bwd_workspace_bytes(int rows, int H) {
+  return b200::rmsnorm_bwd_workspace_bytes(rows, H);
+}
 int b200_rmsnorm_bwd(const void* dy, const void* x, const void* w, const float* rstd, void* dx,
-                     float* dw_f32, int rows, int H, int is_bf16, void* stream) {
-  return b200::rmsnorm_bwd(dy, x, w, rstd, dx, dw_f32, rows, H, is_bf16, S_(stream));
+                     float* dw_f32, int rows, int H, int is_bf16, void* workspace,
+                     size_t workspace_bytes, void* stream) {
+  return b200::rmsnorm_bwd(dy, x, w, rstd, dx, dw_f32, rows, H, is_bf16, workspace, workspace_bytes,
+                           S_(stream));
 }
 int b200_rope(const void* x, void* y, const float* cos_t, const float* sin_t, int B, int S, int NH,
               int D, int backward, int is_bf16, void* stream) {

@@ -300,18 +300,18 @@ split_bf16_kernel(const float* __restrict__ src, long long ld_src, __nv_bfloat16
 
 
 // Shampoo momentum (optimizers/shampoo.py:351-359): m = beta*m + (1-beta)*g ; mhat = m/bias_corr.
-// Emits mhat in fp32 (pass-through part of the update) and as a bf16 hi/lo pair (GEMM operands).
+// Emits out_scale*mhat in fp32 (pass-through part of the update, out_scale = -lr) and as a bf16 hi/lo pair (GEMM operands).
 template <typename G>
 __global__ void __launch_bounds__(EW_THREADS)
 ema_split_kernel(const G* __restrict__ g, float* __restrict__ m, float* __restrict__ out32,
                  __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, long long n,
-                 float beta, float gscale, float inv_bc) {
+                 float beta, float gscale, float inv_bc, float out_scale) {
   for (long long i = (long long)blockIdx.x * EW_THREADS + threadIdx.x; i < n;
        i += (long long)gridDim.x * EW_THREADS) {
     const float mm = beta * m[i] + (1.0f - beta) * ldf(g + i) * gscale;
     m[i] = mm;
     const float mh = mm * inv_bc;
-    out32[i] = mh;
+    out32[i] = mh * out_scale;
     const __nv_bfloat16 h = __float2bfloat16_rn(mh);
     hi[i] = h;
     if (lo) lo[i] = __float2bfloat16_rn(mh - __bfloat162float(h));
@@ -486,15 +486,15 @@ int split_bf16(const float* src, long long ld_src, void* hi, void* lo, long long
 }
 
 int ema_split(const void* g, int g_is_bf16, float* m, float* out32, void* hi, void* lo, long long n,
-              float beta, float gscale, float inv_bc, cudaStream_t stream) {
+              float beta, float gscale, float inv_bc, float out_scale, cudaStream_t stream) {
   B200_CHECK_ARG(n > 0, "ema_split: empty");
   const int grid = ew_grid(n);
   if (g_is_bf16)
     ema_split_kernel<__nv_bfloat16><<<grid, EW_THREADS, 0, stream>>>(
-        (const __nv_bfloat16*)g, m, out32, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, n, beta, gscale, inv_bc);
+        (const __nv_bfloat16*)g, m, out32, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, n, beta, gscale, inv_bc, out_scale);
   else
     ema_split_kernel<float><<<grid, EW_THREADS, 0, stream>>>(
-        (const float*)g, m, out32, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, n, beta, gscale, inv_bc);
+        (const float*)g, m, out32, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, n, beta, gscale, inv_bc, out_scale);
   B200_CHECK_LAUNCH();
   return B200_OK;
 }

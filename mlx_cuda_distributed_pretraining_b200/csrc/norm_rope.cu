@@ -87,13 +87,14 @@ rmsnorm_fwd_kernel(const T* __restrict__ x, const T* __restrict__ w, T* __restri
   }
 }
 
-// dx = rstd * (dy*w - x * rstd^2 * mean(dy*w*x)) ; dw += dy * x * rstd  (fp32 atomics, one per
-// column per block)
+// dx = rstd * (dy*w - x * rstd^2 * mean(dy*w*x)) ; dw partials = sum over this CTA's rows of
+// dy * x * rstd, written to dw_part[blockIdx.x, :] and summed by rmsnorm_dw_reduce_kernel (no atomics:
+// hundreds of CTAs hammering the same H addresses cost 4x the streaming time)
 template <typename T, int NV>
 __global__ void __launch_bounds__(RN_THREADS)
 rmsnorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ w,
-                   const float* __restrict__ rstd_in, T* __restrict__ dx, float* __restrict__ dw,
-                   int rows, int H) {
+                   const float* __restrict__ rstd_in, T* __restrict__ dx,
+                   float* __restrict__ dw_part, int rows, int H) {
   __shared__ float red[4];
   float wv[NV][8], dwv[NV][8];
 #pragma unroll
@@ -140,11 +141,25 @@ rmsnorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* _
 #pragma unroll
   for (int v = 0; v < NV; ++v) {
     const int col = (v * RN_THREADS + threadIdx.x) * 8;
-    if (col < H) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) atomicAdd(dw + col + j, dwv[v][j]);
-    }
+    if (col < H) st8(dw_part + (long long)blockIdx.x * H + col, dwv[v]);
   }
+}
+
+// dw[c] = sum_b dw_part[b, c]
+__global__ void __launch_bounds__(256)
+rmsnorm_dw_reduce_kernel(const float* __restrict__ dw_part, float* __restrict__ dw, int nblocks, int H) {
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c >= H) return;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int b = 0;
+  for (; b + 3 < nblocks; b += 4) {
+    s0 += dw_part[(long long)b * H + c];
+    s1 += dw_part[(long long)(b + 1) * H + c];
+    s2 += dw_part[(long long)(b + 2) * H + c];
+    s3 += dw_part[(long long)(b + 3) * H + c];
+  }
+  for (; b < nblocks; ++b) s0 += dw_part[(long long)b * H + c];
+  dw[c] = (s0 + s1) + (s2 + s3);
 }
 
 // x: [B, S, NH, D]; cos/sin: [S, D/2] fp32. out[2i] = x[2i]*c - x[2i+1]*s ; out[2i+1] = x[2i]*s +
@@ -187,17 +202,21 @@ int rmsnorm_fwd_t(const T* x, const T* w, T* y, float* rstd, int rows, int H, fl
   return B200_OK;
 }
 
+inline int rmsnorm_bwd_grid(int rows) { return rows < num_sms() * 4 ? rows : num_sms() * 4; }
+
 template <typename T>
 int rmsnorm_bwd_t(const T* dy, const T* x, const T* w, const float* rstd, T* dx, float* dw,
-                  int rows, int H, cudaStream_t stream) {
+                  float* dw_part, int rows, int H, cudaStream_t stream) {
   const int nv = (H / 8 + RN_THREADS - 1) / RN_THREADS;
-  const int grid = rows < num_sms() * 4 ? rows : num_sms() * 4;
+  const int grid = rmsnorm_bwd_grid(rows);
   switch (nv) {
-    case 1: rmsnorm_bwd_kernel<T, 1><<<grid, RN_THREADS, 0, stream>>>(dy, x, w, rstd, dx, dw, rows, H); break;
-    case 2: rmsnorm_bwd_kernel<T, 2><<<grid, RN_THREADS, 0, stream>>>(dy, x, w, rstd, dx, dw, rows, H); break;
-    case 3: case 4: rmsnorm_bwd_kernel<T, 4><<<grid, RN_THREADS, 0, stream>>>(dy, x, w, rstd, dx, dw, rows, H); break;
-    default: rmsnorm_bwd_kernel<T, RN_MAX_VEC><<<grid, RN_THREADS, 0, stream>>>(dy, x, w, rstd, dx, dw, rows, H); break;
+    case 1: rmsnorm_bwd_kernel<T, 1><<<grid, RN_THREADS, 0, stream>>>(dy, x, w, rstd, dx, dw_part, rows, H); break;
+    case 2: rmsnorm_bwd_kernel<T, 2><<<grid, RN_THREADS, 0, stream>>>(dy, x, w, rstd, dx, dw_part, rows, H); break;
+    case 3: case 4: rmsnorm_bwd_kernel<T, 4><<<grid, RN_THREADS, 0, stream>>>(dy, x, w, rstd, dx, dw_part, rows, H); break;
+    default: rmsnorm_bwd_kernel<T, RN_MAX_VEC><<<grid, RN_THREADS, 0, stream>>>(dy, x, w, rstd, dx, dw_part, rows, H); break;
   }
+  B200_CHECK_LAUNCH();
+  rmsnorm_dw_reduce_kernel<<<(H + 255) / 256, 256, 0, stream>>>(dw_part, dw, grid, H);
   B200_CHECK_LAUNCH();
   return B200_OK;
 }
@@ -219,18 +238,27 @@ int rmsnorm_fwd(const void* x, const void* w, void* y, float* rstd, int rows, in
                               stream);
 }
 
+size_t rmsnorm_bwd_workspace_bytes(int rows, int H) {
+  return (size_t)rmsnorm_bwd_grid(rows) * H * sizeof(float);
+}
+
 int rmsnorm_bwd(const void* dy, const void* x, const void* w, const float* rstd, void* dx,
-                float* dw, int rows, int H, int is_bf16, cudaStream_t stream) {
+                float* dw, int rows, int H, int is_bf16, void* ws, size_t ws_bytes,
+                cudaStream_t stream) {
   B200_CHECK_ARG(rows > 0 && H > 0 && H % 8 == 0 && H <= RN_THREADS * 8 * RN_MAX_VEC,
                  "rmsnorm_bwd: unsupported shape rows=%d H=%d", rows, H);
   B200_CHECK_ARG(al16(dy) && al16(x) && al16(w) && al16(dx), "rmsnorm_bwd: alignment");
-  B200_CHECK_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * H, stream));
+  if (ws == nullptr || ws_bytes < rmsnorm_bwd_workspace_bytes(rows, H)) {
+    set_error("rmsnorm_bwd: workspace too small (%zu < %zu)", ws_bytes, rmsnorm_bwd_workspace_bytes(rows, H));
+    return B200_ERR_WORKSPACE;
+  }
+  float* part = reinterpret_cast<float*>(ws);
   if (is_bf16)
     return rmsnorm_bwd_t<__nv_bfloat16>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x,
-                                        (const __nv_bfloat16*)w, rstd, (__nv_bfloat16*)dx, dw,
+                                        (const __nv_bfloat16*)w, rstd, (__nv_bfloat16*)dx, dw, part,
                                         rows, H, stream);
   return rmsnorm_bwd_t<float>((const float*)dy, (const float*)x, (const float*)w, rstd, (float*)dx,
-                              dw, rows, H, stream);
+                              dw, part, rows, H, stream);
 }
 
 int rope(const void* x, void* y, const float* cos_t, const float* sin_t, int B, int S, int NH,

@@ -22,6 +22,7 @@ import torch
 from torch import nn
 
 ALIGN = 128  # elements; keeps every group 256-byte aligned in bf16 and 512-byte in fp32
+ROW_PAD = 64  # single-matrix groups are followed by zero rows up to a multiple of this
 
 
 @dataclass
@@ -77,7 +78,11 @@ class ParamStore:
         off = 0
         for g in groups.values():
             g.offset = off
-            off = _round_up(off + g.numel, ALIGN)
+            # single matrices whose row count is not a multiple of 64 (the [V, hidden] embedding with
+            # V = 32003) get zero tail rows reserved, so the tied logits GEMM can read a [V_pad, hidden]
+            # view with an aligned N instead of falling off cuBLAS's fast path (see tied_logits_weight)
+            tail = (_round_up(g.rows, ROW_PAD) - g.rows) * g.cols if g.batch == 1 else 0
+            off = _round_up(off + g.numel + tail, ALIGN)
         self.mat_groups: List[MatGroup] = list(groups.values())
         self.mat_end = off
         self.vec_entries: List[VecEntry] = []
@@ -122,6 +127,31 @@ class ParamStore:
         for s in shape:
             n *= s
         return buf[o:o + n].view(shape)
+
+    def padded_rows_view(self, buf: torch.Tensor, name: str) -> torch.Tensor:
+        """[rows_pad, cols] view of a single-matrix group including its reserved zero tail rows."""
+        o, (r, c) = self.index[name]
+        g = next(g for g in self.mat_groups if name in g.names)
+        if g.batch != 1:
+            raise ValueError(f"{name} is part of a batched group; no tail rows reserved")
+        return buf[o:o + _round_up(r, ROW_PAD) * c].view(_round_up(r, ROW_PAD), c)
+
+    def tied_logits_weight(self, name: str = "embed_tokens.weight") -> Optional[torch.Tensor]:
+        """Autograd leaf aliasing the (row-padded) embedding for the tied logits GEMM h @ E^T
+        (arch/llama.py:401-403).  Its .grad aliases the same flat gradient memory as the
+        parameter's, so both uses of E accumulate into one buffer.  None if no padding is needed."""
+        if name not in self.index:
+            return None
+        o, (r, c) = self.index[name]
+        if r % 8 == 0:
+            return None
+        try:
+            w = self.padded_rows_view(self.shadow if self.mixed else self.master, name)
+        except ValueError:
+            return None
+        leaf = w.detach().requires_grad_(True)
+        leaf.grad = self.padded_rows_view(self.grad, name)
+        return leaf
 
     def group_view(self, buf: torch.Tensor, g: MatGroup) -> torch.Tensor:
         return buf[g.offset:g.offset + g.numel].view(g.batch, g.rows, g.cols)

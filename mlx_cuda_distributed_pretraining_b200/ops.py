@@ -266,9 +266,10 @@ class _RMSNormFn(torch.autograd.Function):
         rows, H = xs.numel() // xs.shape[-1], xs.shape[-1]
         dx = torch.empty_like(xs)
         dw = torch.empty(H, device=xs.device, dtype=torch.float32)
+        ws = torch.empty(int(lib().b200_rmsnorm_bwd_workspace_bytes(rows, H)), device=xs.device, dtype=torch.uint8)
         check(lib().b200_rmsnorm_bwd(dy.data_ptr(), xs.data_ptr(), wc.data_ptr(), rstd.data_ptr(),
                                      dx.data_ptr(), dw.data_ptr(), rows, H, _is_bf16(xs, "x"),
-                                     _stream()), "b200_rmsnorm_bwd")
+                                     ws.data_ptr(), ws.numel(), _stream()), "b200_rmsnorm_bwd")
         return dx, dw.to(ctx.w_dtype), None
 
 
@@ -405,10 +406,10 @@ def gemm_raw(a_mn: bool, b_mn: bool, M: int, N: int, K: int, batch: int,
                                _ptr(beta_vec), int(force_bn), _stream()), "b200_gemm_bf16")
 
 
-def ema_split(g, m, out32, hi, lo, beta: float, gscale: float, inv_bc: float) -> None:
+def ema_split(g, m, out32, hi, lo, beta: float, gscale: float, inv_bc: float, out_scale: float = 1.0) -> None:
     check(lib().b200_ema_split(g.data_ptr(), _is_bf16(g, "g"), m.data_ptr(), out32.data_ptr(),
                                hi.data_ptr(), _ptr(lo), g.numel(), float(beta), float(gscale),
-                               float(inv_bc), _stream()), "b200_ema_split")
+                               float(inv_bc), float(out_scale), _stream()), "b200_ema_split")
 
 
 def graft_update(p32, p16, pre, d, numel: int, batch: int, coef, coef_d, decay: float) -> None:

@@ -204,8 +204,10 @@ class Shampoo:
         else:
             torch.mul(gsrc[:end].float(), -lr * gs, out=self._d[:end])
         inv_bc = 1.0 / (1.0 - hp.beta1 ** t) if hp.use_bias_correction else 1.0
+        # pre = -lr * mhat (the reference's `update = -lr * preconditioned_grad`, shampoo.py:365); the
+        # preconditioned blocks are overwritten below with -lr * PL mhat PR
         ops.ema_split(gsrc[:end], self._mom[:end], self._pre[:end], self._mh[:end], self._ml[:end], hp.beta1, gs,
-                      inv_bc)
+                      inv_bc, -lr)
         if gsrc.dtype != torch.bfloat16:
             if self._g16 is None:
                 self._g16 = torch.empty(store.total, dtype=torch.bfloat16, device=store.device)
@@ -242,7 +244,7 @@ class Shampoo:
                     # pre[:k1,:k2] = T @ PR  written straight into the update buffer (ldd = cols)
                     pre = self._pre[lo:lo + n]
                     self._gemm3(False, True, k1, k2, k2, b, Th, Tl, k2, k1 * k2, s.PRh, s.PRl, k2, k2 * k2,
-                                None, c, rc, pre, c, rc, 1.0, 0.0)
+                                None, c, rc, pre, c, rc, -lr, 0.0)
             self._graft_and_apply(store, lo, rc, b, lr, decay)
         for e in store.vec_entries:
             self._graft_and_apply(store, e.offset, e.numel, 1, lr, decay)
@@ -253,10 +255,11 @@ class Shampoo:
         n1, n2 = self._n1[:batch], self._n2[:batch]
         ops.sumsq_raw(pre, n1, numel, batch)
         ops.sumsq_raw(d, n2, numel, batch)
-        pn, gn = n1.sqrt(), n2.sqrt()      # ||pre||, ||graft step||  ([batch] scalars)
-        # upd = -lr*pre ; grafted: upd*(gn/||upd||) = -pre*gn/||pre|| ; gn==0 -> keep upd ; ||pre||==0 -> graft
-        coef = torch.where(pn == 0, torch.zeros_like(pn), torch.where(gn == 0, torch.full_like(pn, -lr), -gn / pn))
-        coef_d = (pn == 0).float()
+        sn, gn = n1.sqrt(), n2.sqrt()      # ||upd|| with upd = -lr*pre (held in self._pre), ||graft step||
+        # _apply_grafting (shampoo.py:297-312): sn==0 -> graft step ; gn==0 -> upd ; else upd*(gn/sn).
+        # fp32 sqrt(sum(x^2)) overflows exactly like mx.linalg.norm would
+        coef = torch.where(sn == 0, torch.zeros_like(sn), torch.where(gn == 0, torch.ones_like(sn), gn / sn))
+        coef_d = (sn == 0).float()
         p16 = store.shadow[lo:lo + n] if store.mixed else None
         ops.graft_update(store.master[lo:lo + n], p16, pre, d, numel, batch, coef.contiguous(), coef_d.contiguous(),
                          decay)

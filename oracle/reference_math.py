@@ -414,7 +414,9 @@ class ShampooOracle:
                 m_, n_ = min(g.shape[0], cap), min(g.shape[1], cap)
                 pre[:m_, :n_] = st["preconditioners"][0] @ mom[:m_, :n_] @ st["preconditioners"][1]
             upd = -lr * pre
-            sn, gn = torch.linalg.norm(upd), torch.linalg.norm(graft)
+            # mx.linalg.norm (shampoo.py:300-301) is sqrt(sum(x^2)) in fp32: it overflows to inf when the
+            # literal "inverse root" blows the preconditioned step up (D10), which zeroes the grafted step
+            sn, gn = torch.sqrt((upd * upd).sum()), torch.sqrt((graft * graft).sum())
             if sn == 0:
                 upd = graft
             elif gn != 0:

@@ -51,8 +51,8 @@ def tiny_config(name="smoke", optimizer="muon", mixed=True, **over):
 def smoke(verbose: bool = True) -> dict:
     sys.path.insert(0, str(ROOT))
     from oracle import reference_math as R
-    from . import ops
-    from .core.training import Config, Trainer
+    from mlx_cuda_distributed_pretraining_b200 import ops
+    from mlx_cuda_distributed_pretraining_b200.core.training import Config, Trainer
 
     ops.require_device()
     out = {}

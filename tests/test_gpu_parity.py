@@ -1,0 +1,278 @@
+"""-m gpu: the CUDA path, called through the C ABI, against the oracle and the golden vectors.
+
+Tolerances (relative Frobenius error unless noted; see DESIGN.md section "Parity"):
+  fp32 elementwise kernels            1e-6      (same formula, fp32)
+  bf16-output kernels                 4e-3      (one bf16 rounding of the result, 2^-8 relative)
+  GEMM, fp32 out, bf16 operands       2e-6      (exact products, fp32 accumulation order)
+  attention fwd/bwd (bf16 I/O)        1e-2      (north_star: "stated fp tolerance")
+  Newton-Schulz 5 steps, bf16 operands 3e-2     (measured ~1e-2)
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import reference_math as R  # noqa: E402
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu(), torch.as_tensor(np.asarray(b)).double() if not torch.is_tensor(b) else b.detach().double().cpu()
+    # the 1e-4 floor keeps exact-zero references (e.g. dQ of a single-key softmax) meaningful
+    return float((a - b).norm() / (b.norm() + 1e-4))
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from mlx_cuda_distributed_pretraining_b200 import ops as o
+    o.require_device()
+    return o
+
+
+# ------------------------------------------------------------------------------------------------
+# dense contraction engine
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, True), (True, False)])
+@pytest.mark.parametrize("M,N,K,batch,bn", [(128, 256, 64, 1, 0), (200, 328, 136, 3, 0), (256, 512, 1000, 2, 128),
+                                           (384, 256, 520, 2, 256), (8, 8, 8, 1, 0), (1000, 64, 72, 1, 0)])
+def test_gemm_layouts(ops, a_mn, b_mn, M, N, K, batch, bn):
+    torch.manual_seed(M + N + K)
+    if (a_mn and M % 8) or (b_mn and N % 8) or (not a_mn and K % 8) or (not b_mn and K % 8):
+        pytest.skip("leading dimension must be a multiple of 8")
+    a = torch.randn((batch, K, M) if a_mn else (batch, M, K), device="cuda").to(torch.bfloat16)
+    b = torch.randn((batch, K, N) if b_mn else (batch, N, K), device="cuda").to(torch.bfloat16)
+    ref = torch.bmm(a.float().transpose(1, 2) if a_mn else a.float(), b.float() if b_mn else b.float().transpose(1, 2))
+    out = ops.gemm(a, b, a_mn=a_mn, b_mn=b_mn, out_dtype=torch.float32, force_bn=bn)
+    assert rel(out, ref) < 2e-6
+
+
+def test_gemm_epilogue(ops):
+    torch.manual_seed(0)
+    batch, M, N, K = 3, 256, 512, 320
+    a = torch.randn(batch, M, K, device="cuda").to(torch.bfloat16)
+    b = torch.randn(batch, N, K, device="cuda").to(torch.bfloat16)
+    c = torch.randn(batch, M, N, device="cuda").to(torch.bfloat16)
+    av, bv = torch.rand(batch, device="cuda") + 0.5, torch.rand(batch, device="cuda") + 0.5
+    prod = torch.bmm(a.float(), b.float().transpose(1, 2))
+    out = ops.gemm(a, b, c=c, alpha=0.5, beta=-1.25, alpha_vec=av, beta_vec=bv)
+    assert rel(out, 0.5 * av[:, None, None] * prod - 1.25 * bv[:, None, None] * c.float()) < 4e-3
+    c32 = torch.randn(batch, M, N, device="cuda")
+    out = ops.gemm(a, b, c=c32, alpha=2.0, beta=0.75, out_dtype=torch.float32)
+    assert rel(out, 2.0 * prod + 0.75 * c32) < 2e-6
+    # in-place accumulate (C aliases D), as the bf16x3 Shampoo products do
+    acc = c32.clone()
+    ops.gemm(a, b, c=acc, out=acc, alpha=1.0, beta=1.0)
+    assert rel(acc, prod + c32) < 2e-6
+
+
+def test_gemm_rejects_bad_arguments(ops):
+    from mlx_cuda_distributed_pretraining_b200._lib import B200Error
+    a = torch.zeros(16, 12, device="cuda", dtype=torch.bfloat16)   # K = 12: 24-byte rows, not TMA-able
+    with pytest.raises(B200Error):
+        ops.gemm(a, a)
+    with pytest.raises(ValueError):
+        ops.gemm(a.float(), a.float())
+
+
+# ------------------------------------------------------------------------------------------------
+# Newton-Schulz
+# ------------------------------------------------------------------------------------------------
+def test_newton_schulz_golden(ops, golden):
+    for tag in ("wide", "tall", "square", "batched"):
+        g = torch.from_numpy(golden[f"ns_{tag}_in"])
+        if g.shape[-1] % 8:
+            continue
+        x = ops.zeropower_via_newtonschulz5(g.cuda(), 5)
+        assert rel(x, golden[f"ns_{tag}_out"]) < 3e-2, tag
+
+
+@pytest.mark.parametrize("shape", [(2, 256, 512), (2, 512, 256), (1, 1024, 1024), (3, 512, 1024), (1, 2816, 1024),
+                                   (1, 1024, 2816), (1, 1000, 256), (1, 136, 72), (1, 32003, 1024)])
+def test_newton_schulz_vs_oracle(ops, shape):
+    torch.manual_seed(1)
+    g = torch.randn(*shape) * 0.02
+    x = ops.zeropower_via_newtonschulz5(g.cuda())
+    assert rel(x, R.newton_schulz5(g.double())) < 3e-2
+    # full-size property: singular values of the result in [0.66, 1.16] for
+    # full-rank rectangular Gaussians (square Gaussians are near-singular, so skip them)
+    if shape[1] != shape[2] and max(shape[1:]) <= 4096:
+        sv = torch.linalg.svdvals(x[0].float().cpu())
+        assert 0.64 < sv.min() and sv.max() < 1.18, (sv.min(), sv.max())
+
+
+def test_newton_schulz_transpose_equivariance_and_steps(ops):
+    torch.manual_seed(2)
+    g = (torch.randn(1, 384, 640) * 0.1).cuda()
+    x = ops.zeropower_via_newtonschulz5(g)
+    xt = ops.zeropower_via_newtonschulz5(g.transpose(1, 2).contiguous())
+    assert rel(xt.transpose(1, 2), x) < 2e-2          # tall path == transpose of wide path
+    for steps in (1, 2, 4):
+        xs = ops.zeropower_via_newtonschulz5(g, steps=steps)
+        assert rel(xs, R.newton_schulz5(g.cpu().double(), steps)) < 3e-2
+    z = ops.zeropower_via_newtonschulz5(torch.zeros(1, 64, 128, device="cuda"))
+    assert torch.count_nonzero(z) == 0 and torch.isfinite(z.float()).all()   # eps keeps 0/0 away
+
+
+# ------------------------------------------------------------------------------------------------
+# elementwise optimizer kernels
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("gdt", [torch.bfloat16, torch.float32])
+def test_muon_momentum_and_scales(ops, gdt):
+    torch.manual_seed(3)
+    batch, r, c = 3, 64, 136
+    g = torch.randn(batch, r, c, device="cuda").to(gdt)
+    buf = torch.randn(batch, r, c, device="cuda")
+    b0 = buf.clone()
+    u = torch.empty(batch, r, c, device="cuda", dtype=torch.bfloat16)
+    ss = torch.empty(batch, device="cuda")
+    for nesterov in (True, False):
+        buf.copy_(b0)
+        ops.muon_momentum(g, buf, u, ss, 0.95, nesterov, 0.5)
+        gf = g.float() * 0.5
+        bref = 0.05 * gf + 0.95 * b0
+        uref = gf + 0.95 * bref if nesterov else bref
+        assert rel(buf, bref) < 1e-6 and rel(u, uref) < 4e-3 and rel(ss, (uref ** 2).sum(dim=(1, 2))) < 1e-5
+    inv, inv2 = ops.ns_scales(ss, 1e-7)
+    assert rel(inv, 1 / (ss.sqrt() + 1e-7)) < 1e-6 and rel(inv2, inv * inv) < 1e-6
+
+
+def test_adamw_sgd_axpy_clip(ops):
+    torch.manual_seed(4)
+    n = 4099
+    for bc in (False, True):
+        p = torch.randn(n, device="cuda"); p0 = p.clone()
+        g = torch.randn(n, device="cuda")
+        m = torch.randn(n, device="cuda") * 0.1; v = torch.rand(n, device="cuda") * 0.1
+        m0, v0 = m.clone(), v.clone()
+        p16 = torch.empty(n, device="cuda", dtype=torch.bfloat16)
+        t = 3
+        bc1, bc2 = (1 - 0.9 ** t, 1 - 0.95 ** t) if bc else (1.0, 1.0)
+        ops.adamw(p, p16, g, m, v, 1e-2, 0.9, 0.95, 1e-8, 0.1, bc1, bc2)
+        mr = 0.9 * m0 + 0.1 * g; vr = 0.95 * v0 + 0.05 * g * g
+        pr = p0 * (1 - 1e-2 * 0.1) - (1e-2 / bc1) * mr / (vr.sqrt() / bc2 ** 0.5 + 1e-8)
+        assert rel(p, pr) < 1e-6 and rel(m, mr) < 1e-6 and rel(v, vr) < 1e-6 and rel(p16, pr) < 4e-3
+    p = torch.randn(n, device="cuda"); p0 = p.clone(); buf = torch.randn(n, device="cuda"); b0 = buf.clone()
+    ops.sgd_momentum(p, None, g, buf, 0.95, True, 0.01)
+    br = 0.05 * g + 0.95 * b0
+    assert rel(p, p0 - 0.01 * (g + 0.95 * br)) < 1e-6
+    x = torch.randn(n, device="cuda").to(torch.bfloat16); p0 = p.clone()
+    ops.axpy_update(p, None, x, -0.1)
+    assert rel(p, p0 - 0.1 * x.float()) < 1e-6
+    acc = torch.randn(n, device="cuda"); a0 = acc.clone()
+    g16 = (torch.randn(n, device="cuda") * 2).to(torch.bfloat16)
+    ops.clip_accum(g16, acc, 1.0, 0.125, False)       # core/training.py:1664-1666,1671-1680
+    assert torch.equal(acc, a0 + g16.float().clamp(-1, 1) * 0.125)
+    ops.clip_accum(g16, acc, 0.0, 0.5, True)
+    assert torch.equal(acc, g16.float() * 0.5)
+
+
+# ------------------------------------------------------------------------------------------------
+# RMSNorm / RoPE
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dt,tol", [(torch.bfloat16, 4e-3), (torch.float32, 2e-6)])
+@pytest.mark.parametrize("H", [128, 1024, 2048, 5120])
+def test_rmsnorm_fwd_bwd(ops, dt, tol, H):
+    torch.manual_seed(5)
+    x = torch.randn(3, 37, H, device="cuda").to(dt).requires_grad_(True)
+    w = (torch.rand(H, device="cuda") + 0.5).to(dt).requires_grad_(True)
+    y = ops.rmsnorm(x, w, 1e-5)
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    xr, wr = x.detach().float().cpu().requires_grad_(True), w.detach().float().cpu().requires_grad_(True)
+    yr = R.rmsnorm(xr, wr, 1e-5)
+    yr.backward(dy.float().cpu())
+    assert rel(y, yr) < tol and rel(x.grad, xr.grad) < tol and rel(w.grad, wr.grad) < max(tol, 5e-6)
+
+
+def test_rmsnorm_golden(ops, golden):
+    x, w = torch.from_numpy(golden["rms_x"]).cuda(), torch.from_numpy(golden["rms_w"]).cuda()
+    assert rel(ops.rmsnorm(x, w, 1e-5), golden["rms_y"]) < 2e-6
+
+
+@pytest.mark.parametrize("D", [16, 64, 128])
+def test_rope_fwd_bwd(ops, D):
+    torch.manual_seed(6)
+    x = torch.randn(2, 33, 4, D, device="cuda").to(torch.bfloat16).requires_grad_(True)
+    cos_t, sin_t = ops.rope_tables(33, D, 10000.0, "cuda")
+    y = ops.rope(x, cos_t, sin_t)
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    xr = x.detach().float().cpu().requires_grad_(True)
+    yr = R.rope(xr, 10000.0)
+    yr.backward(dy.float().cpu())
+    assert rel(y, yr) < 4e-3 and rel(x.grad, xr.grad) < 4e-3
+    # rotation preserves pair norms: ||y|| == ||x|| (size-independent property)
+    assert abs(float(y.float().norm() / x.float().norm()) - 1) < 2e-3
+
+
+# ------------------------------------------------------------------------------------------------
+# attention
+# ------------------------------------------------------------------------------------------------
+def _attn_case(ops, B, S, H, Hk, D, causal, seed=7):
+    torch.manual_seed(seed)
+    q = torch.randn(B, S, H, D, device="cuda").to(torch.bfloat16).requires_grad_(True)
+    k = torch.randn(B, S, Hk, D, device="cuda").to(torch.bfloat16).requires_grad_(True)
+    v = torch.randn(B, S, Hk, D, device="cuda").to(torch.bfloat16).requires_grad_(True)
+    o = ops.attention(q, k, v, D ** -0.5, causal)
+    do = torch.randn_like(o)
+    o.backward(do)
+    qr, kr, vr = (t.detach().float().cpu().requires_grad_(True) for t in (q, k, v))
+    orf = R.attention(qr, kr, vr, D ** -0.5, R.causal_mask(S) if causal else None)
+    orf.backward(do.float().cpu())
+    return (rel(o, orf), rel(q.grad, qr.grad), rel(k.grad, kr.grad), rel(v.grad, vr.grad))
+
+
+@pytest.mark.parametrize("B,S,H,Hk,D,causal", [
+    (2, 16, 4, 4, 32, True), (2, 16, 4, 1, 32, True), (2, 16, 4, 2, 32, True),   # the reference's own test matrix
+    (1, 1, 2, 1, 64, True), (1, 127, 2, 2, 64, True), (1, 129, 2, 2, 64, True), (1, 200, 2, 2, 64, False),
+    (2, 512, 4, 2, 64, True), (1, 384, 4, 1, 128, True), (1, 300, 2, 2, 128, False), (2, 256, 8, 8, 16, True),
+    (1, 1024, 16, 8, 64, True)])
+def test_attention_fwd_bwd_vs_oracle(ops, B, S, H, Hk, D, causal):
+    errs = _attn_case(ops, B, S, H, Hk, D, causal)
+    assert max(errs) < 1e-2, errs
+
+
+def test_attention_golden(ops, golden):
+    for tag in ("mha", "mqa", "gqa"):
+        q, k, v = (torch.from_numpy(golden[f"attn_{tag}_{n}"]).cuda().to(torch.bfloat16) for n in "qkv")
+        assert rel(ops.attention(q, k, v, 32 ** -0.5, True), golden[f"attn_{tag}_causal"]) < 1e-2, tag
+        assert rel(ops.attention(q, k, v, 32 ** -0.5, False), golden[f"attn_{tag}_nomask"]) < 1e-2, tag
+
+
+def test_attention_properties_full_size(ops):
+    """BASELINE sizes (C2 layer: B16 S1024 H16/8 D64), checked through size-independent properties:
+    causality (outputs before t do not depend on tokens >= t), GQA == explicit kv repeat,
+    softmax rows sum to one (V = 1 gives O = 1), and linearity of dV in dO."""
+    torch.manual_seed(8)
+    B, S, H, Hk, D = 16, 1024, 16, 8, 64
+    q = torch.randn(B, S, H, D, device="cuda").to(torch.bfloat16)
+    k = torch.randn(B, S, Hk, D, device="cuda").to(torch.bfloat16)
+    v = torch.randn(B, S, Hk, D, device="cuda").to(torch.bfloat16)
+    o = ops.attention(q, k, v, D ** -0.5, True)
+    k2, v2 = k.clone(), v.clone()
+    k2[:, 700:], v2[:, 700:] = torch.randn_like(k2[:, 700:]), torch.randn_like(v2[:, 700:])
+    o2 = ops.attention(q, k2, v2, D ** -0.5, True)
+    assert torch.equal(o[:, :700], o2[:, :700])                       # causality, bit-exact
+    kr, vr = k.repeat_interleave(H // Hk, dim=2), v.repeat_interleave(H // Hk, dim=2)
+    assert torch.equal(ops.attention(q, kr, vr, D ** -0.5, True), o)  # GQA head sharing, bit-exact
+    ones = ops.attention(q, k, torch.ones_like(v), D ** -0.5, True)
+    assert float((ones.float() - 1).abs().max()) < 8e-3               # rows of P sum to 1
+    qg, kg, vg = (t.clone().requires_grad_(True) for t in (q, k, v))
+    og = ops.attention(qg, kg, vg, D ** -0.5, True)
+    d1, d2 = torch.randn_like(og), torch.randn_like(og)
+    (g1,) = torch.autograd.grad(og, vg, d1, retain_graph=True)
+    (g2,) = torch.autograd.grad(og, vg, d2, retain_graph=True)
+    (g12,) = torch.autograd.grad(og, vg, (d1.float() + d2.float()).to(torch.bfloat16))
+    assert rel(g12, g1.float() + g2.float()) < 1e-2                   # dV is linear in dO
+
+
+def test_attention_unsupported_inputs_fail_loudly(ops):
+    from mlx_cuda_distributed_pretraining_b200.arch.flash_attention import FlashAttention
+    attn = FlashAttention(64, 4, 2, 16).cuda().to(torch.bfloat16)
+    x = torch.randn(1, 8, 64, device="cuda", dtype=torch.bfloat16)
+    with pytest.raises(NotImplementedError):
+        attn(x, mask=torch.zeros(1, 1, 8, 8, device="cuda"))
+    with pytest.raises(ValueError):
+        ops.attention(torch.zeros(1, 8, 2, 256, device="cuda", dtype=torch.bfloat16),
+                      torch.zeros(1, 8, 2, 256, device="cuda", dtype=torch.bfloat16),
+                      torch.zeros(1, 8, 2, 256, device="cuda", dtype=torch.bfloat16))
