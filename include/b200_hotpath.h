@@ -39,7 +39,9 @@ unsigned long long b200_launch_count(void); /* kernels launched by this library 
  * a_mn=0: A is [M,K] row-major (K-major);  a_mn=1: A is stored [K,M] row-major (MN-major)
  * b_mn=0: B is [N,K] row-major (K-major);  b_mn=1: B is stored [K,N] row-major (MN-major)
  * A,B bf16; C,D bf16 (out_f32=0) or f32 (out_f32=1); accumulate fp32 in TMEM.
- * alpha_vec/beta_vec: optional per-batch device scalars (NULL = 1).  force_bn: 0 auto | 128 | 256.
+ * alpha_vec/beta_vec: optional per-batch device scalars (NULL = 1).
+ * force_bn: 0 auto | 128 | 256 tile width | 1256 = 256-wide tiles and the caller asserts D == D^T
+ * (M == N, bf16 out): only tiles on/above the diagonal are computed, the rest mirror-written.
  */
 int b200_gemm_bf16(int a_mn, int b_mn, int M, int N, int K, int batch,
                    const void* A, long long lda, long long strideA,

@@ -300,6 +300,12 @@ int dispatch_out(bool out_f32, int bn, const CUtensorMap& tmA, const CUtensorMap
 
 }  // namespace
 
+int gemm_bf16_2cta(bool a_mn, bool b_mn, int M, int N, int K, int batch, const void* A, long long lda,
+                   long long strideA, const void* B, long long ldb, long long strideB, const void* C,
+                   long long ldc, long long strideC, void* D, long long ldd, long long strideD, bool out_f32,
+                   float alpha, float beta, const float* alpha_vec, const float* beta_vec, int bn,
+                   int symmetric, cudaStream_t stream);
+
 // Internal C++ entry (also used by the Newton-Schulz / Shampoo drivers).
 int gemm_bf16(bool a_mn, bool b_mn, int M, int N, int K, int batch, const void* A, long long lda,
               long long strideA, const void* B, long long ldb, long long strideB, const void* C,
@@ -321,6 +327,26 @@ int gemm_bf16(bool a_mn, bool b_mn, int M, int N, int K, int batch, const void* 
                      strideC % out_vec == 0,
                  "gemm: batch strides must keep 16-byte alignment");
 
+  // CTA-pair path (gemm_tc2.cu): 256 x BN tiles with tcgen05.mma.cta_group::2 whenever there are at
+  // least two 128-row blocks; halves the L2->SM operand traffic per flop.
+  {
+    static const bool force_1cta = [] {
+      const char* e = getenv("B200_GEMM_1CTA");
+      return e != nullptr && e[0] == '1';
+    }();
+    if (!force_1cta && M > 128 && num_sms() >= 2) {
+      int bn2 = 256;
+      const long long t256 = (long long)((M + 255) / 256) * ((N + 255) / 256) * batch;
+      // force_bn: 0 auto | 128 | 256 | 1256 = 256-wide tiles + symmetric-output mode (D == D^T)
+      const int symmetric = force_bn == 1256 ? 1 : 0;
+      if (symmetric) force_bn = 256;
+      if (N <= 128 || t256 < (num_sms() / 2) * 3 / 4) bn2 = 128;
+      if (force_bn == 128 || force_bn == 256) bn2 = force_bn;
+      return gemm_bf16_2cta(a_mn, b_mn, M, N, K, batch, A, lda, strideA, B, ldb, strideB, C, ldc, strideC, D,
+                            ldd, strideD, out_f32, alpha, beta, alpha_vec, beta_vec, bn2, symmetric, stream);
+    }
+  }
+
   // tile-N choice: 256 feeds the tensor pipe at full rate; fall back to 128 when the 256-wide
   // grid would leave most SMs idle.
   int bn = 256;
@@ -329,6 +355,7 @@ int gemm_bf16(bool a_mn, bool b_mn, int M, int N, int K, int batch, const void* 
     if (N <= 128 || t256 < num_sms() / 2) bn = 128;
   }
   if (force_bn == 128 || force_bn == 256) bn = force_bn;
+  if (force_bn == 1256) bn = 256;  // symmetric hint is only exploited by the CTA-pair kernel
 
   CUtensorMap tmA, tmB;
   {

@@ -20,6 +20,10 @@ int gemm_bf16(bool a_mn, bool b_mn, int M, int N, int K, int batch, const void* 
 
 static inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
 
+// A = X X^T and B = bA + cAA are symmetric: only tiles on or above the diagonal are computed and
+// the rest mirror-written (force_bn code understood by gemm_bf16; ignored when it cannot apply)
+static constexpr int kSym = 1256;
+
 size_t newton_schulz_workspace_bytes(int batch, int rows, int cols, int steps) {
   const size_t m = rows < cols ? rows : cols;
   size_t bytes = 2 * align256((size_t)batch * m * m * 2);
@@ -59,14 +63,14 @@ int newton_schulz(const void* x_in, void* x_out, int batch, int rows, int cols, 
     // G1
     if (!tall)
       rc_ = gemm_bf16(false, false, m, m, cols, batch, cur, cols, rc, cur, cols, rc, nullptr, 0, 0,
-                      Abuf, m, mm, false, 1.0f, 0.0f, s2, nullptr, 0, stream);
+                      Abuf, m, mm, false, 1.0f, 0.0f, s2, nullptr, kSym, stream);
     else
       rc_ = gemm_bf16(true, true, m, m, rows, batch, cur, cols, rc, cur, cols, rc, nullptr, 0, 0,
-                      Abuf, m, mm, false, 1.0f, 0.0f, s2, nullptr, 0, stream);
+                      Abuf, m, mm, false, 1.0f, 0.0f, s2, nullptr, kSym, stream);
     if (rc_) return rc_;
     // G2: B = b*A + c*A*A
     rc_ = gemm_bf16(false, false, m, m, m, batch, Abuf, m, mm, Abuf, m, mm, Abuf, m, mm, Bbuf, m,
-                    mm, false, c, b, nullptr, nullptr, 0, stream);
+                    mm, false, c, b, nullptr, nullptr, kSym, stream);
     if (rc_) return rc_;
     // G3
     if (!tall)
