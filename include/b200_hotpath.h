@@ -122,6 +122,20 @@ int b200_rmsnorm_bwd(const void* dy, const void* x, const void* w, const float* 
 int b200_rope(const void* x, void* y, const float* cos_t, const float* sin_t, int B, int S, int NH,
               int D, int backward, int is_bf16, void* stream);
 
+/* ---- block-adjacent fused elementwise steps ------------------------------------
+ * arch/llama.py:151: y = gate * sigmoid(up) * 2 and its adjoint; bf16, n % 8 == 0 */
+int b200_glu_fwd(const void* gate, const void* up, void* y, long long n, void* stream);
+int b200_glu_bwd(const void* dy, const void* gate, const void* up, void* dgate, void* dup, long long n,
+                 void* stream);
+/* core/training.py:1226-1234: per-row cross entropy of bf16 logits [rows, ld] (first V columns valid),
+ * computed in fp32: row_lse = logsumexp, row_loss = (target != pad_token) ? lse - logit[target] : 0.
+ * ce_bwd overwrites logits with row_scale[row] * (softmax - onehot(target)) (0 in columns >= V and in
+ * rows whose target is pad_token). */
+int b200_ce_fwd(const void* logits, long long ld, const long long* targets, int rows, int V,
+                long long pad_token, float* row_loss, float* row_lse, void* stream);
+int b200_ce_bwd(void* logits, long long ld, const long long* targets, int rows, int V, long long pad_token,
+                const float* row_lse, const float* row_scale, void* stream);
+
 /* ---- fused causal / GQA attention (arch/flash_attention.py:97-156 + its autograd) --------------
  * q: bf16 [B,S,H,D], k,v: bf16 [B,S,Hk,D] (q head h uses kv head h/(H/Hk), flash_attention.py:102-120)
  * o: bf16 [B,S,H,D]; lse: f32 [B,H,S] (natural-log sum-exp of scaled, masked scores)

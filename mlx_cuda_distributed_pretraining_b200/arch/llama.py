@@ -71,7 +71,7 @@ class MLP(nn.Module):
         self.down_proj = nn.Linear(intermediate_size, hidden_size, bias=use_bias)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        return self.down_proj(self.gate_proj(x) * torch.sigmoid(self.up_proj(x)) * 2)
+        return self.down_proj(ops.glu(self.gate_proj(x), self.up_proj(x)))
 
 
 class AttentionModule(nn.Module):
@@ -134,13 +134,37 @@ class Model(nn.Module):
         self._tied_w = None  # padded alias of the embedding for the logits GEMM (set lazily)
         self.lm_head = None if args.tie_word_embeddings else nn.Linear(args.hidden_size, args.vocab_size, bias=False)
 
-    def forward(self, inputs: torch.Tensor, position_ids=None, attention_mask=None) -> torch.Tensor:
+    def hidden_states(self, inputs: torch.Tensor, position_ids=None, attention_mask=None) -> torch.Tensor:
         B, S = inputs.shape
         mask = CausalMask(S) if attention_mask is None else attention_mask
         h = self.embed_tokens(inputs)
         for layer in self.layers:
             h = layer(h, mask=mask, position_ids=position_ids)
-        h = self.norm(h)
+        return self.norm(h)
+
+    def padded_logits(self, inputs: torch.Tensor):
+        """(logits [B*S, ld], V) with ld >= V, ld % 8 == 0 when the fused cross-entropy can take them
+        (tied + row-padded embedding alias, or an aligned vocabulary); else (None, V)."""
+        if self.logit_scale is not None:
+            return None, self.vocab_size
+        h = self.hidden_states(inputs)
+        store = getattr(self, "_b200_store", None)
+        if self.lm_head is None and store is not None and self._tied_w is None:
+            w = store.tied_logits_weight()
+            self._tied_w = w if w is not None else False
+        if self.lm_head is not None:
+            w = self.lm_head.weight
+        elif self._tied_w is not None and self._tied_w is not False:
+            w = self._tied_w
+        else:
+            w = self.embed_tokens.weight
+        if w.shape[0] % 8 != 0 or h.dtype != torch.bfloat16:
+            return None, self.vocab_size
+        logits = torch.nn.functional.linear(h, w)
+        return logits.view(-1, logits.shape[-1]), self.vocab_size
+
+    def forward(self, inputs: torch.Tensor, position_ids=None, attention_mask=None) -> torch.Tensor:
+        h = self.hidden_states(inputs, position_ids, attention_mask)
         if self.lm_head is None:
             store = getattr(self, "_b200_store", None)
             if store is not None and self._tied_w is None:

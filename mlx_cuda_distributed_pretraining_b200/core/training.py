@@ -479,11 +479,16 @@ class Trainer:
         max_ctx = self.config.model.attention.get("max_position_embeddings", 2048)
         if inputs.shape[1] > max_ctx:
             inputs, targets = inputs[:, :max_ctx], targets[:, :max_ctx]
+        pad_mask = targets != self.tokenizer.PAD_TOKEN
+        ntoks = pad_mask.sum()
+        logits2d, V = model.padded_logits(inputs) if hasattr(model, "padded_logits") else (None, None)
+        if logits2d is not None:
+            # fused path: fp32 log-sum-exp over bf16 logits, pad mask applied per row, no fp32 [B,S,V] copy
+            rows = ops.cross_entropy_rows(logits2d, targets.reshape(-1).contiguous(), V, self.tokenizer.PAD_TOKEN)
+            return rows.sum() / ntoks, ntoks
         logits = model(inputs).float()  # loss always in fp32 (core/training.py:1226)
         ce = torch.nn.functional.cross_entropy(logits.view(-1, logits.shape[-1]), targets.reshape(-1),
                                                reduction="none").view(targets.shape)
-        pad_mask = targets != self.tokenizer.PAD_TOKEN
-        ntoks = pad_mask.sum()
         return (ce * pad_mask).sum() / ntoks, ntoks
 
     def _to_device(self, batch: torch.Tensor) -> torch.Tensor:

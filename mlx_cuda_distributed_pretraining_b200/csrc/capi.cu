@@ -46,6 +46,12 @@ int rmsnorm_bwd(const void* dy, const void* x, const void* w, const float* rstd,
                 cudaStream_t stream);
 int rope(const void* x, void* y, const float* cos_t, const float* sin_t, int B, int S, int NH,
          int D, int backward, int is_bf16, cudaStream_t stream);
+int glu_fwd(const void* g, const void* u, void* y, long long n, cudaStream_t stream);
+int glu_bwd(const void* dy, const void* g, const void* u, void* dg, void* du, long long n, cudaStream_t stream);
+int ce_fwd(const void* logits, long long ld, const long long* targets, int rows, int V, long long pad_token,
+           float* row_loss, float* row_lse, cudaStream_t stream);
+int ce_bwd(void* logits, long long ld, const long long* targets, int rows, int V, long long pad_token,
+           const float* row_lse, const float* row_scale, cudaStream_t stream);
 int attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int B, int S, int H,
              int Hk, int D, float scale, int causal, cudaStream_t stream);
 size_t attn_bwd_workspace_bytes(int B, int S, int H, int Hk, int D);
@@ -157,6 +163,20 @@ int b200_rmsnorm_bwd(const void* dy, const void* x, const void* w, const float* 
 int b200_rope(const void* x, void* y, const float* cos_t, const float* sin_t, int B, int S, int NH,
               int D, int backward, int is_bf16, void* stream) {
   return b200::rope(x, y, cos_t, sin_t, B, S, NH, D, backward, is_bf16, S_(stream));
+}
+int b200_glu_fwd(const void* g, const void* u, void* y, long long n, void* stream) {
+  return b200::glu_fwd(g, u, y, n, S_(stream));
+}
+int b200_glu_bwd(const void* dy, const void* g, const void* u, void* dg, void* du, long long n, void* stream) {
+  return b200::glu_bwd(dy, g, u, dg, du, n, S_(stream));
+}
+int b200_ce_fwd(const void* logits, long long ld, const long long* targets, int rows, int V,
+                long long pad_token, float* row_loss, float* row_lse, void* stream) {
+  return b200::ce_fwd(logits, ld, targets, rows, V, pad_token, row_loss, row_lse, S_(stream));
+}
+int b200_ce_bwd(void* logits, long long ld, const long long* targets, int rows, int V, long long pad_token,
+                const float* row_lse, const float* row_scale, void* stream) {
+  return b200::ce_bwd(logits, ld, targets, rows, V, pad_token, row_lse, row_scale, S_(stream));
 }
 int b200_attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int B, int S,
                   int H, int Hk, int D, float scale, int causal, void* stream) {

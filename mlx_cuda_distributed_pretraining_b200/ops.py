@@ -421,3 +421,66 @@ def graft_update(p32, p16, pre, d, numel: int, batch: int, coef, coef_d, decay: 
 def sumsq_raw(x: torch.Tensor, out: torch.Tensor, numel: int, batch: int, zero_first: bool = True) -> None:
     check(lib().b200_sumsq(x.data_ptr(), _is_bf16(x, "x"), out.data_ptr(), numel, batch, int(zero_first),
                            _stream()), "b200_sumsq")
+
+
+# ------------------------------------------------------------------------------------------------
+# block-adjacent fused elementwise steps
+# ------------------------------------------------------------------------------------------------
+class _GluFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, gate, up):
+        g, u = gate.contiguous(), up.contiguous()
+        y = torch.empty_like(g)
+        check(lib().b200_glu_fwd(g.data_ptr(), u.data_ptr(), y.data_ptr(), g.numel(), _stream()), "b200_glu_fwd")
+        ctx.save_for_backward(g, u)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        g, u = ctx.saved_tensors
+        dy = dy.contiguous()
+        dg, du = torch.empty_like(g), torch.empty_like(u)
+        check(lib().b200_glu_bwd(dy.data_ptr(), g.data_ptr(), u.data_ptr(), dg.data_ptr(), du.data_ptr(),
+                                 g.numel(), _stream()), "b200_glu_bwd")
+        return dg, du
+
+
+def glu(gate: torch.Tensor, up: torch.Tensor) -> torch.Tensor:
+    """gate * sigmoid(up) * 2 (arch/llama.py:151).  bf16 tensors with numel % 8 == 0 take the fused
+    kernel; other dtypes (fp32 configs) use the same formula through torch ops."""
+    if gate.dtype == torch.bfloat16 and gate.is_cuda and gate.numel() % 8 == 0:
+        return _GluFn.apply(gate, up)
+    return gate * torch.sigmoid(up) * 2
+
+
+class _CrossEntropyFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits2d, targets, V, pad_token):
+        rows, ld = logits2d.shape
+        row_loss = torch.empty(rows, device=logits2d.device, dtype=torch.float32)
+        row_lse = torch.empty(rows, device=logits2d.device, dtype=torch.float32)
+        check(lib().b200_ce_fwd(logits2d.data_ptr(), ld, targets.data_ptr(), rows, V, int(pad_token),
+                                row_loss.data_ptr(), row_lse.data_ptr(), _stream()), "b200_ce_fwd")
+        ctx.save_for_backward(logits2d, targets, row_lse)
+        ctx.V, ctx.pad = V, int(pad_token)
+        return row_loss
+
+    @staticmethod
+    def backward(ctx, d_row_loss):
+        logits2d, targets, row_lse = ctx.saved_tensors
+        rows, ld = logits2d.shape
+        scale = d_row_loss.contiguous().float()
+        # in place: the logits buffer becomes d(loss)/d(logits); its producer (the logits GEMM) does
+        # not need its own output for backward
+        check(lib().b200_ce_bwd(logits2d.data_ptr(), ld, targets.data_ptr(), rows, ctx.V, ctx.pad,
+                                row_lse.data_ptr(), scale.data_ptr(), _stream()), "b200_ce_bwd")
+        return logits2d, None, None, None
+
+
+def cross_entropy_rows(logits2d: torch.Tensor, targets: torch.Tensor, V: int, pad_token: int) -> torch.Tensor:
+    """Per-row masked cross entropy of bf16 logits [rows, ld>=V] (contiguous, ld % 8 == 0), fp32 math;
+    rows whose target is pad_token contribute 0 (the pad mask of core/training.py:1230-1232)."""
+    _need(logits2d, torch.bfloat16, "logits")
+    if targets.dtype != torch.int64 or not targets.is_contiguous():
+        raise ValueError("targets must be contiguous int64")
+    return _CrossEntropyFn.apply(logits2d, targets, int(V), int(pad_token))

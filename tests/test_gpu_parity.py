@@ -276,3 +276,48 @@ def test_attention_unsupported_inputs_fail_loudly(ops):
         ops.attention(torch.zeros(1, 8, 2, 256, device="cuda", dtype=torch.bfloat16),
                       torch.zeros(1, 8, 2, 256, device="cuda", dtype=torch.bfloat16),
                       torch.zeros(1, 8, 2, 256, device="cuda", dtype=torch.bfloat16))
+
+
+# ------------------------------------------------------------------------------------------------
+# block-adjacent fused steps: GLU activation and cross entropy
+# ------------------------------------------------------------------------------------------------
+def test_glu_fwd_bwd(ops):
+    torch.manual_seed(9)
+    g = torch.randn(3, 50, 264, device="cuda").to(torch.bfloat16).requires_grad_(True)
+    u = torch.randn(3, 50, 264, device="cuda").to(torch.bfloat16).requires_grad_(True)
+    y = ops.glu(g, u)
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    gr, ur = g.detach().float().cpu().requires_grad_(True), u.detach().float().cpu().requires_grad_(True)
+    yr = gr * torch.sigmoid(ur) * 2            # arch/llama.py:151
+    yr.backward(dy.float().cpu())
+    assert rel(y, yr) < 4e-3 and rel(g.grad, gr.grad) < 4e-3 and rel(u.grad, ur.grad) < 4e-3
+
+
+def test_glu_golden(ops, golden):
+    lin = torch.nn.functional.linear
+    x = torch.from_numpy(golden["mlp_x"]).cuda().to(torch.bfloat16)
+    w = {k: torch.from_numpy(golden[f"mlp_{k}"]).cuda().to(torch.bfloat16) for k in ("gate_proj", "up_proj", "down_proj")}
+    y = lin(ops.glu(lin(x, w["gate_proj"]), lin(x, w["up_proj"])), w["down_proj"])
+    assert rel(y, golden["mlp_y"]) < 2e-2
+
+
+@pytest.mark.parametrize("rows,V,ld", [(64, 259, 264), (33, 32003, 32064), (16, 512, 512), (5, 8, 8)])
+def test_cross_entropy_fwd_bwd(ops, rows, V, ld):
+    torch.manual_seed(10)
+    pad = V - 3
+    full = torch.zeros(rows, ld, device="cuda", dtype=torch.bfloat16)
+    full[:, :V] = (torch.randn(rows, V, device="cuda") * 3).to(torch.bfloat16)
+    targets = torch.randint(0, V, (rows,), device="cuda")
+    targets[::7] = pad                                   # some padded positions
+    logits = full.clone().requires_grad_(True)
+    loss_rows = ops.cross_entropy_rows(logits, targets, V, pad)
+    w = torch.rand(rows, device="cuda") + 0.5
+    (loss_rows * w).sum().backward()
+    ref_in = full[:, :V].float().cpu().requires_grad_(True)
+    ce = torch.nn.functional.cross_entropy(ref_in, targets.cpu(), reduction="none") * (targets.cpu() != pad)
+    (ce * w.cpu()).sum().backward()
+    assert rel(loss_rows, ce) < 1e-5
+    assert float(loss_rows[targets == pad].abs().max()) == 0.0
+    assert rel(logits.grad[:, :V], ref_in.grad) < 4e-3
+    assert torch.count_nonzero(logits.grad[:, V:]) == 0
