@@ -12,7 +12,8 @@
 // Working transposed puts keys on the 128 TMEM lanes, so P^T / dS^T rows are written by their
 // owning thread straight into K-major swizzled smem tiles that feed the dV / dK MMAs, and the
 // same dS^T tile is read as an MN-major A operand for dQ -- no smem transposes anywhere.
-// Warp roles: warp 0 TMA, warp 1 MMA issue, warps 2-5 softmax / dQ drain / dK,dV epilogue.
+// Warp roles: warp 0 TMA, warp 1 MMA issue, warps 2-9 (two warpgroups, half the columns each)
+// softmax / dQ drain / dK,dV epilogue.
 #include "common.cuh"
 #include "host.h"
 
@@ -23,7 +24,7 @@ int make_bshd_map(CUtensorMap* tm, const void* base, int B, int S, int heads, in
 
 namespace {
 
-constexpr int BWD_THREADS = 192;
+constexpr int BWD_THREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2-9: two softmax warpgroups
 constexpr int BT = 128;  // tile size along both queries and keys
 
 template <int D>
@@ -130,9 +131,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_init(q_empty(s), 1);
     }
     mbar_init(s_full, 1);
-    mbar_init(pds_full, 4);
+    mbar_init(pds_full, 8);
     mbar_init(dq_full, 1);
-    mbar_init(dq_empty, 4);
+    mbar_init(dq_empty, 8);
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
@@ -227,7 +228,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const int key = k0 + row;
     const uint32_t t_lane = tmem_base + (uint32_t(qd * 32) << 16);
     const float sl2 = p.scale * 1.4426950408889634f;
-    const int tid = threadIdx.x - 64;  // 0..127 (warp-major, not TMEM-lane order)
+    const int tid = threadIdx.x - 64;  // 0..255 (warp-major, not TMEM-lane order)
+    // Two warpgroups share every tile: both see all 128 key rows (TMEM lane quarter = warp % 4) and
+    // each takes half of the columns, so every SM sub-partition holds two softmax warps that hide
+    // each other's TMEM / MUFU latency.
+    const int wg = (warp - 2) >> 2;
 
     for (int it = 0; it < n_it; ++it) {
       const int h = hk * G + it / n_qt;
@@ -235,17 +240,20 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       float* lse2 = lse_s + (it & 1) * 256;
       float* dlt = lse2 + 128;
       {
-        const int q = q0 + tid;
+        const int qi = tid & 127;
+        const int q = q0 + qi;
         const long long idx = ((long long)b * p.H + h) * p.S + q;
-        lse2[tid] = q < p.S ? p.lse[idx] * 1.4426950408889634f : INFINITY;
-        dlt[tid] = q < p.S ? p.delta[idx] : 0.f;
+        if (tid < 128)
+          lse2[qi] = q < p.S ? p.lse[idx] * 1.4426950408889634f : INFINITY;
+        else
+          dlt[qi] = q < p.S ? p.delta[idx] : 0.f;
       }
-      named_bar_sync(1, 128);
+      named_bar_sync(1, 256);
       mbar_wait(s_full, it & 1u);
       tc_fence_after_sync();
       const bool diag = p.causal && q0 == k0;  // tiles are aligned: only the diagonal tile is cut
 #pragma unroll 1
-      for (int c0 = 0; c0 < BT; c0 += 32) {
+      for (int c0 = wg * (BT / 2); c0 < (wg + 1) * (BT / 2); c0 += 32) {
         uint32_t vs[32], vd[32];
         tmem_ld_32x32b_x32(t_lane + Cfg::TM_S + c0, vs);
         tmem_ld_32x32b_x32(t_lane + Cfg::TM_DP + c0, vd);
@@ -277,7 +285,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const int q = q0 + row;
         float* dst = p.dq_acc + (((long long)b * p.S + q) * p.H + h) * D;
 #pragma unroll 1
-        for (int c0 = 0; c0 < D; c0 += 32) {
+        for (int c0 = wg * (D / 2); c0 < (wg + 1) * (D / 2); c0 += 32) {
           uint32_t v[32];
           tmem_ld_32x32b_x32(t_lane + Cfg::TM_DQ + c0, v);
           tmem_ld_wait();
@@ -300,7 +308,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       __nv_bfloat16* out = (which == 0 ? p.dv : p.dk) + (((long long)b * p.S + key) * p.Hk + hk) * D;
       const uint32_t col = which == 0 ? Cfg::TM_DV : Cfg::TM_DK;
 #pragma unroll 1
-      for (int c0 = 0; c0 < D; c0 += 32) {
+      for (int c0 = wg * (D / 2); c0 < (wg + 1) * (D / 2); c0 += 32) {
         uint32_t v[32];
         tmem_ld_32x32b_x32(t_lane + col + c0, v);
         tmem_ld_wait();

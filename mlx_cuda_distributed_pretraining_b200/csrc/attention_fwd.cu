@@ -5,12 +5,13 @@
 // tiled with an online softmax, so the [B,H,S,S] score tensor the reference materialises (:134)
 // never exists.  Also emits LSE = log sum exp(scaled masked scores) for the backward pass.
 //
-// One CTA per (128-query tile, head, batch); 192 threads:
+// One CTA per (128-query tile, head, batch); 320 threads:
 //   warp 0      TMA producer: Q once, then K/V tiles (128 keys) through a 2-stage ring
 //   warp 1      tcgen05.mma issuer: S = Q K^T -> TMEM (double-buffered), O += P V -> TMEM
-//   warps 2-5   softmax: one query row per thread (TMEM lane = row). Two passes over S in TMEM
-//               (row max, then exp2 / row sum), P written to smem as a K-major 128B-swizzled bf16
-//               operand, O rescaled in TMEM only when a row max moved.
+//   warps 2-9   softmax, two warpgroups: each thread owns one query row (TMEM lane) x 64 of the 128
+//               key columns; scores stay in registers between row max (exchanged through smem) and
+//               exp2; P written to smem as a K-major 128B-swizzled bf16 operand; O rescaled in TMEM
+//               only when a row max moved.
 // S(j+1) is issued before P(j) is waited for, so QK^T of the next tile overlaps the softmax.
 #include "common.cuh"
 #include "host.h"
@@ -21,7 +22,7 @@ namespace {
 
 constexpr int ATT_BQ = 128;
 constexpr int ATT_BKV = 128;
-constexpr int FWD_THREADS = 192;
+constexpr int FWD_THREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2-9: two softmax warpgroups
 constexpr int KV_STAGES = 2;
 
 template <int D>
@@ -33,8 +34,9 @@ struct FwdCfg {
   static constexpr int OFF_V = OFF_K + KV_STAGES * TILE_BYTES;
   static constexpr int OFF_P = OFF_V + KV_STAGES * TILE_BYTES;
   static constexpr int OFF_BAR = OFF_P + P_BYTES;
+  static constexpr int OFF_RED = OFF_BAR + 256;  // [2][2][128] row-max exchange + [2][128] row-sum exchange
   // >113.5 KB of smem also pins one CTA per SM, so the 512-column TMEM allocation never contends
-  static constexpr int SMEM_BYTES = (OFF_BAR + 256 + 1024) > 120 * 1024 ? (OFF_BAR + 256 + 1024) : 120 * 1024;
+  static constexpr int SMEM_BYTES = (OFF_RED + 3072 + 1024) > 120 * 1024 ? (OFF_RED + 3072 + 1024) : 120 * 1024;
   static constexpr int TMEM_COLS = 512;
   static constexpr int TM_S0 = 0, TM_S1 = 128, TM_O = 256;
 };
@@ -75,6 +77,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const uint32_t p_full = bar + 8u * 13;
   const uint32_t pv_done = bar + 8u * 14;
   const uint32_t tmem_slot = bar + 8u * 15;
+  float* red_s = reinterpret_cast<float*>(smem_raw + (sbase - smem_u32(smem_raw)) + Cfg::OFF_RED);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -100,9 +103,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_init(v_full(s), 1);
       mbar_init(v_empty(s), 1);
       mbar_init(s_full(s), 1);
-      mbar_init(s_empty(s), 4);
+      mbar_init(s_empty(s), 8);
     }
-    mbar_init(p_full, 4);
+    mbar_init(p_full, 8);
     mbar_init(pv_done, 1);
     fence_mbar_init();
   }
@@ -175,38 +178,53 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
   } else {
     // ------------------------------------ softmax warps -------------------------------------
-    const int qd = warp & 3;  // TMEM lane quarter accessible to this warp
+    // Two warpgroups (warps 2-5, 6-9) share every S tile: both cover all 128 query rows (TMEM lane
+    // quarter = warp % 4), each owns 64 of the 128 key columns and half of O's columns.  Each SM
+    // sub-partition therefore runs two softmax warps that hide each other's TMEM / MUFU latency, and a
+    // thread's 64 scores stay in registers between the max and the exp (one TMEM pass).
+    const int qd = warp & 3;
+    const int wg = (warp - 2) >> 2;
     const int row = qd * 32 + lane;
     const int q_row = q0 + row;
     const uint32_t t_lane = tmem_base + (uint32_t(qd * 32) << 16);
     const float sl2 = p.scale * 1.4426950408889634f;
+    const int cbase = wg * 64;
+    constexpr int OH = D / 2;  // O columns owned by this warpgroup
     float m = -INFINITY, l = 0.f;
 
     for (int j = 0; j < n_kv; ++j) {
       const int sb = j & 1;
-      const uint32_t t_s = t_lane + (sb ? Cfg::TM_S1 : Cfg::TM_S0);
-      const int k0 = j * ATT_BKV;
-      const bool need_mask = (p.causal && k0 + ATT_BKV - 1 > q0) || (k0 + ATT_BKV > p.S);
+      const uint32_t t_s = t_lane + (sb ? Cfg::TM_S1 : Cfg::TM_S0) + cbase;
+      const int k0 = j * ATT_BKV + cbase;
+      const bool need_mask = (p.causal && j * ATT_BKV + ATT_BKV - 1 > q0) || (j * ATT_BKV + ATT_BKV > p.S);
       const int kmax = p.causal ? (q_row < p.S - 1 ? q_row : p.S - 1) : p.S - 1;  // last valid key
 
       mbar_wait(s_full(sb), (j >> 1) & 1u);
       tc_fence_after_sync();
-      // pass 1: row max
+      uint32_t v[64];
+      tmem_ld_32x32b_x32(t_s, v);
+      tmem_ld_32x32b_x32(t_s + 32, v + 32);
+      tmem_ld_wait();
+      // the scores now live in registers: hand the S buffer back to the tensor core right away
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_empty(sb));
+
       float mx = -INFINITY;
-#pragma unroll 1
-      for (int c0 = 0; c0 < ATT_BKV; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(t_s + c0, v);
-        tmem_ld_wait();
-        if (need_mask) {
+      if (need_mask) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (k0 + c0 + i <= kmax) mx = fmaxf(mx, __uint_as_float(v[i]));
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+        for (int i = 0; i < 64; ++i) {
+          if (k0 + i > kmax) v[i] = __float_as_uint(-INFINITY);
+          mx = fmaxf(mx, __uint_as_float(v[i]));
         }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 64; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
       }
+      float* mslot = red_s + (j & 1) * 256;
+      mslot[wg * 128 + row] = mx;
+      named_bar_sync(1, 256);
+      mx = fmaxf(mx, mslot[(wg ^ 1) * 128 + row]);
       const float m_new = fmaxf(m, mx);
       const float alpha = fast_exp2((m - m_new) * sl2);
       const float mb = m_new * sl2;
@@ -217,80 +235,70 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tc_fence_after_sync();
         if (__any_sync(0xffffffffu, m_new > m)) {
 #pragma unroll 1
-          for (int c0 = 0; c0 < D; c0 += 32) {
-            uint32_t v[32];
-            tmem_ld_32x32b_x32(t_lane + Cfg::TM_O + c0, v);
+          for (int c0 = 0; c0 < OH; c0 += 32) {
+            uint32_t o[32];
+            tmem_ld_32x32b_x32(t_lane + Cfg::TM_O + wg * OH + c0, o);
             tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
-            tmem_st_32x32b_x32(t_lane + Cfg::TM_O + c0, v);
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st_32x32b_x32(t_lane + Cfg::TM_O + wg * OH + c0, o);
           }
           tmem_st_wait();
         }
       }
-      // pass 2: probabilities -> bf16 P tile (K-major, 128B swizzle), row sum
+      // probabilities -> bf16 P tile (K-major, 128B swizzle): this warpgroup fills 64-column block `wg`
       float rs = 0.f;
-#pragma unroll 1
-      for (int c0 = 0; c0 < ATT_BKV; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(t_s + c0, v);
-        tmem_ld_wait();
-        float pr[32];
+      const uint32_t blk = sP + wg * 16384 + row * 128;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float e = fast_exp2(fmaf(__uint_as_float(v[i]), sl2, -mb));
-          if (need_mask && (k0 + c0 + i > kmax)) e = 0.f;
-          pr[i] = e;
-          rs += e;
-        }
-        const uint32_t blk = sP + (c0 >> 6) * 16384 + row * 128;
+      for (int g = 0; g < 8; ++g) {
+        float e[8];
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const int chunk = ((c0 & 63) >> 3) + g;
-          const uint32_t addr = blk + ((chunk ^ (row & 7)) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr),
-                       "r"(pack_bf16x2(pr[g * 8 + 0], pr[g * 8 + 1])),
-                       "r"(pack_bf16x2(pr[g * 8 + 2], pr[g * 8 + 3])),
-                       "r"(pack_bf16x2(pr[g * 8 + 4], pr[g * 8 + 5])),
-                       "r"(pack_bf16x2(pr[g * 8 + 6], pr[g * 8 + 7]))
-                       : "memory");
+        for (int i = 0; i < 8; ++i) {
+          e[i] = fast_exp2(fmaf(__uint_as_float(v[g * 8 + i]), sl2, -mb));
+          rs += e[i];
         }
+        const uint32_t addr = blk + ((g ^ (row & 7)) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pack_bf16x2(e[0], e[1])),
+                     "r"(pack_bf16x2(e[2], e[3])), "r"(pack_bf16x2(e[4], e[5])), "r"(pack_bf16x2(e[6], e[7]))
+                     : "memory");
       }
       l = l * alpha + rs;
       m = m_new;
-      // publish: S buffer consumed, P tile + rescaled O visible to the tensor core (async proxy)
+      // publish: P tile + rescaled O visible to the tensor core (async proxy)
       tc_fence_before_sync();
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(s_empty(sb));
-        mbar_arrive(p_full);
-      }
+      if (lane == 0) mbar_arrive(p_full);
     }
 
     // --------------------------------------- epilogue ---------------------------------------
+    // each warpgroup holds the row sum of its own 64-column halves: combine them once
+    float* lslot = red_s + 512;
+    lslot[wg * 128 + row] = l;
+    named_bar_sync(1, 256);
+    l += lslot[(wg ^ 1) * 128 + row];
     mbar_wait(pv_done, (n_kv - 1) & 1u);
     tc_fence_after_sync();
     const float inv_l = 1.0f / l;
-    __nv_bfloat16* orow = p.o + (((long long)b * p.S + q_row) * p.H + h) * D;
+    __nv_bfloat16* orow = p.o + (((long long)b * p.S + q_row) * p.H + h) * D + wg * OH;
 #pragma unroll 1
-    for (int c0 = 0; c0 < D; c0 += 32) {
-      uint32_t v[32];
-      tmem_ld_32x32b_x32(t_lane + Cfg::TM_O + c0, v);
+    for (int c0 = 0; c0 < OH; c0 += 32) {
+      uint32_t o[32];
+      tmem_ld_32x32b_x32(t_lane + Cfg::TM_O + wg * OH + c0, o);
       tmem_ld_wait();
       if (q_row < p.S) {
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           uint4 o4;
-          o4.x = pack_bf16x2(__uint_as_float(v[g * 8 + 0]) * inv_l, __uint_as_float(v[g * 8 + 1]) * inv_l);
-          o4.y = pack_bf16x2(__uint_as_float(v[g * 8 + 2]) * inv_l, __uint_as_float(v[g * 8 + 3]) * inv_l);
-          o4.z = pack_bf16x2(__uint_as_float(v[g * 8 + 4]) * inv_l, __uint_as_float(v[g * 8 + 5]) * inv_l);
-          o4.w = pack_bf16x2(__uint_as_float(v[g * 8 + 6]) * inv_l, __uint_as_float(v[g * 8 + 7]) * inv_l);
+          o4.x = pack_bf16x2(__uint_as_float(o[g * 8 + 0]) * inv_l, __uint_as_float(o[g * 8 + 1]) * inv_l);
+          o4.y = pack_bf16x2(__uint_as_float(o[g * 8 + 2]) * inv_l, __uint_as_float(o[g * 8 + 3]) * inv_l);
+          o4.z = pack_bf16x2(__uint_as_float(o[g * 8 + 4]) * inv_l, __uint_as_float(o[g * 8 + 5]) * inv_l);
+          o4.w = pack_bf16x2(__uint_as_float(o[g * 8 + 6]) * inv_l, __uint_as_float(o[g * 8 + 7]) * inv_l);
           stg128(orow + c0 + g * 8, o4);
         }
       }
     }
-    if (q_row < p.S) p.lse[((long long)b * p.H + h) * p.S + q_row] = m * p.scale + logf(l);
+    if (wg == 0 && q_row < p.S) p.lse[((long long)b * p.H + h) * p.S + q_row] = m * p.scale + logf(l);
   }
 
   tc_fence_before_sync();
