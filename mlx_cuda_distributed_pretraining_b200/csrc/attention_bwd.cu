@@ -14,6 +14,8 @@
 // same dS^T tile is read as an MN-major A operand for dQ -- no smem transposes anywhere.
 // Warp roles: warp 0 TMA, warp 1 MMA issue, warps 2-9 (two warpgroups, half the columns each)
 // softmax / dQ drain / dK,dV epilogue.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "host.h"
 
@@ -21,6 +23,9 @@ namespace b200 {
 
 int make_bshd_map(CUtensorMap* tm, const void* base, int B, int S, int heads, int D, int box_rows,
                   bool f32);
+int launch_attn_bwd64(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV,
+                      const CUtensorMap& tmDO, const float* lse, const float* delta, float* dq_acc, void* dk,
+                      void* dv, int B, int S, int H, int Hk, float scale, int causal, cudaStream_t stream);
 
 namespace {
 
@@ -56,7 +61,14 @@ struct BwdArgs {
   int B, S, H, Hk;
   float scale;
   int causal;
+  long long* trace;  // optional clock64 trace of CTA 0 (debug; nullptr in production)
 };
+
+#define BWD_TRACE(slot)                                                                   \
+  do {                                                                                    \
+    if (p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && it < 16) \
+      p.trace[it * 16 + (slot)] = clock64();                                              \
+  } while (0)
 
 __device__ __forceinline__ float ex2(float x) {
   float y;
@@ -105,7 +117,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const uint32_t dq_empty = bar + 8u * 8;
   const uint32_t tmem_slot = bar + 8u * 9;
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = warp_idx_uniform();
   const int lane = threadIdx.x & 31;
 
   const int kt = blockIdx.x;  // kv tile (tile 0 sees every query tile under the causal mask)
@@ -157,7 +169,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const uint32_t ph = (it / ST) & 1u;
         const int h = hk * G + it / n_qt;
         const int q0 = (qt_first + it % n_qt) * BT;
+        BWD_TRACE(6);
         mbar_wait(q_empty(st), ph ^ 1u);
+        BWD_TRACE(7);
         mbar_arrive_expect_tx(q_full(st), 2 * Cfg::TILE_BYTES);
 #pragma unroll
         for (int db = 0; db < D / 64; ++db) {
@@ -167,58 +181,71 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ---------------------------------- MMA issuer --------------------------------------
+    {
+      // ---------------- MMA issuer: the whole warp runs the control flow (uniform), -------------
+      // ---------------- one elected lane issues tcgen05.mma / commit ---------------------------
       constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, false, false);  // K-major x K-major
       constexpr uint32_t idesc_kv = make_idesc_bf16(128, D, false, true);    // K-major x MN-major
       constexpr uint32_t idesc_dq = make_idesc_bf16(128, D, true, true);     // MN-major x MN-major
       mbar_wait(kv_full, 0);
       for (int it = 0; it < n_it; ++it) {
         const int st = it % ST;
+        if (lane == 0) BWD_TRACE(8);
         mbar_wait(q_full(st), (it / ST) & 1u);
         if (Cfg::ALIAS_DQ && it > 0) mbar_wait(dq_empty, (it - 1) & 1u);
         tc_fence_after_sync();
-        // S^T = K Q^T and dP^T = V dO^T   (M = keys, N = queries, K = head dim)
+        if (lane == 0) BWD_TRACE(9);
+        if (elect_one()) {
+          // S^T = K Q^T and dP^T = V dO^T   (M = keys, N = queries, K = head dim)
 #pragma unroll
-        for (int kk = 0; kk < D / 16; ++kk) {
-          const uint32_t off = (kk >> 2) * 16384 + (kk & 3) * 32;
-          umma_bf16_ss(tmem_base + Cfg::TM_S, make_smem_desc_sw128(sK + off, 0, 1024),
-                       make_smem_desc_sw128(sQ(st) + off, 0, 1024), idesc_s, kk != 0);
-        }
+          for (int kk = 0; kk < D / 16; ++kk) {
+            const uint32_t off = (kk >> 2) * 16384 + (kk & 3) * 32;
+            umma_bf16_ss(tmem_base + Cfg::TM_S, make_smem_desc_sw128(sK + off, 0, 1024),
+                         make_smem_desc_sw128(sQ(st) + off, 0, 1024), idesc_s, kk != 0);
+          }
 #pragma unroll
-        for (int kk = 0; kk < D / 16; ++kk) {
-          const uint32_t off = (kk >> 2) * 16384 + (kk & 3) * 32;
-          umma_bf16_ss(tmem_base + Cfg::TM_DP, make_smem_desc_sw128(sV + off, 0, 1024),
-                       make_smem_desc_sw128(sDO(st) + off, 0, 1024), idesc_s, kk != 0);
+          for (int kk = 0; kk < D / 16; ++kk) {
+            const uint32_t off = (kk >> 2) * 16384 + (kk & 3) * 32;
+            umma_bf16_ss(tmem_base + Cfg::TM_DP, make_smem_desc_sw128(sV + off, 0, 1024),
+                         make_smem_desc_sw128(sDO(st) + off, 0, 1024), idesc_s, kk != 0);
+          }
+          umma_commit(s_full);
         }
-        umma_commit(s_full);
+        __syncwarp();
+        if (lane == 0) BWD_TRACE(10);
 
         mbar_wait(pds_full, it & 1u);
+        if (lane == 0) BWD_TRACE(11);
         if (!Cfg::ALIAS_DQ && it > 0) mbar_wait(dq_empty, (it - 1) & 1u);
         tc_fence_after_sync();
-        // dV += P^T dO ; dK += dS^T Q   (M = keys, N = head dim, K = queries)
+        if (lane == 0) BWD_TRACE(12);
+        if (elect_one()) {
+          // dV += P^T dO ; dK += dS^T Q   (M = keys, N = head dim, K = queries)
 #pragma unroll
-        for (int kk = 0; kk < BT / 16; ++kk) {
-          const uint32_t aoff = (kk >> 2) * 16384 + (kk & 3) * 32;
-          umma_bf16_ss(tmem_base + Cfg::TM_DV, make_smem_desc_sw128(sPT + aoff, 0, 1024),
-                       make_smem_desc_sw128(sDO(st) + kk * 2048, 16384, 1024), idesc_kv,
-                       (it | kk) != 0);
-        }
+          for (int kk = 0; kk < BT / 16; ++kk) {
+            const uint32_t aoff = (kk >> 2) * 16384 + (kk & 3) * 32;
+            umma_bf16_ss(tmem_base + Cfg::TM_DV, make_smem_desc_sw128(sPT + aoff, 0, 1024),
+                         make_smem_desc_sw128(sDO(st) + kk * 2048, 16384, 1024), idesc_kv,
+                         (it | kk) != 0);
+          }
 #pragma unroll
-        for (int kk = 0; kk < BT / 16; ++kk) {
-          const uint32_t aoff = (kk >> 2) * 16384 + (kk & 3) * 32;
-          umma_bf16_ss(tmem_base + Cfg::TM_DK, make_smem_desc_sw128(sDS + aoff, 0, 1024),
-                       make_smem_desc_sw128(sQ(st) + kk * 2048, 16384, 1024), idesc_kv,
-                       (it | kk) != 0);
-        }
-        // dQ = dS K   (M = queries, N = head dim, K = keys): dS^T tile read as an MN-major A
+          for (int kk = 0; kk < BT / 16; ++kk) {
+            const uint32_t aoff = (kk >> 2) * 16384 + (kk & 3) * 32;
+            umma_bf16_ss(tmem_base + Cfg::TM_DK, make_smem_desc_sw128(sDS + aoff, 0, 1024),
+                         make_smem_desc_sw128(sQ(st) + kk * 2048, 16384, 1024), idesc_kv,
+                         (it | kk) != 0);
+          }
+          // dQ = dS K   (M = queries, N = head dim, K = keys): dS^T tile read as an MN-major A
 #pragma unroll
-        for (int kk = 0; kk < BT / 16; ++kk) {
-          umma_bf16_ss(tmem_base + Cfg::TM_DQ, make_smem_desc_sw128(sDS + kk * 2048, 16384, 1024),
-                       make_smem_desc_sw128(sK + kk * 2048, 16384, 1024), idesc_dq, kk != 0);
+          for (int kk = 0; kk < BT / 16; ++kk) {
+            umma_bf16_ss(tmem_base + Cfg::TM_DQ, make_smem_desc_sw128(sDS + kk * 2048, 16384, 1024),
+                         make_smem_desc_sw128(sK + kk * 2048, 16384, 1024), idesc_dq, kk != 0);
+          }
+          umma_commit(q_empty(st));
+          umma_commit(dq_full);
         }
-        umma_commit(q_empty(st));
-        umma_commit(dq_full);
+        __syncwarp();
+        if (lane == 0) BWD_TRACE(13);
       }
     }
   } else {
@@ -239,6 +266,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const int q0 = (qt_first + it % n_qt) * BT;
       float* lse2 = lse_s + (it & 1) * 256;
       float* dlt = lse2 + 128;
+      if (threadIdx.x == 64) BWD_TRACE(0);
       {
         const int qi = tid & 127;
         const int q = q0 + qi;
@@ -249,8 +277,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           dlt[qi] = q < p.S ? p.delta[idx] : 0.f;
       }
       named_bar_sync(1, 256);
+      if (threadIdx.x == 64) BWD_TRACE(1);
       mbar_wait(s_full, it & 1u);
       tc_fence_after_sync();
+      if (threadIdx.x == 64) BWD_TRACE(2);
       const bool diag = p.causal && q0 == k0;  // tiles are aligned: only the diagonal tile is cut
 #pragma unroll 1
       for (int c0 = wg * (BT / 2); c0 < (wg + 1) * (BT / 2); c0 += 32) {
@@ -277,10 +307,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(pds_full);
+      if (threadIdx.x == 64) BWD_TRACE(3);
 
       // drain dQ (TMEM lanes are query rows here) into the fp32 accumulator
       mbar_wait(dq_full, it & 1u);
       tc_fence_after_sync();
+      if (threadIdx.x == 64) BWD_TRACE(4);
       {
         const int q = q0 + row;
         float* dst = p.dq_acc + (((long long)b * p.S + q) * p.H + h) * D;
@@ -300,6 +332,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(dq_empty);
+      if (threadIdx.x == 64) BWD_TRACE(5);
     }
 
     // dK / dV: the last dq_full commit covers every MMA issued before it
@@ -455,7 +488,19 @@ int attn_bwd(const void* q, const void* k, const void* v, const void* o, const v
   a.Hk = Hk;
   a.scale = scale;
   a.causal = causal;
-  rc = D == 64 ? launch_bwd<64>(tmQ, tmK, tmV, tmDO, a, stream) : launch_bwd<128>(tmQ, tmK, tmV, tmDO, a, stream);
+  {
+    // debug: B200_ATTN_TRACE=<device pointer, hex> makes CTA 0 record clock64 stamps (tools/attn_trace.py)
+    const char* e = getenv("B200_ATTN_TRACE");
+    a.trace = e ? reinterpret_cast<long long*>(strtoull(e, nullptr, 16)) : nullptr;
+  }
+  static const bool force_v1 = [] {
+    const char* e = getenv("B200_ATTN_BWD_V1");
+    return e != nullptr && e[0] == '1';
+  }();
+  if (D == 64 && !force_v1)  // software-pipelined head_dim-64 kernel (attention_bwd64.cu)
+    rc = launch_attn_bwd64(tmQ, tmK, tmV, tmDO, lse, delta, dq_acc, dk, dv, B, S, H, Hk, scale, causal, stream);
+  else
+    rc = D == 64 ? launch_bwd<64>(tmQ, tmK, tmV, tmDO, a, stream) : launch_bwd<128>(tmQ, tmK, tmV, tmDO, a, stream);
   if (rc) return rc;
   {
     const long long nvec = n / 8;

@@ -1,0 +1,422 @@
+// Attention backward, head_dim 64, software-pipelined variant of attention_bwd.cu (same math, same
+// transposed formulation, same GQA handling; see that file's header).
+//
+// What the r01 clock trace of the first version showed (tools/attn_trace.py): one (kv tile, q tile)
+// iteration took ~7000 cycles against 1280 cycles of tensor work, because everything was a serial
+// chain on the softmax threads: softmax 2400 -> wait for dV/dK/dQ MMAs 1500 -> dQ drain 2100 (row-per-lane
+// red.global = 32 L2 transactions per warp instruction).  This version
+//   * double-buffers the P^T / dS^T operand tiles, and issues S,dP(it+1) BEFORE dV,dK,dQ(it), so the
+//     softmax threads of iteration it+1 run while the tensor core finishes iteration it;
+//   * drains dQ(it-1) through an fp32 smem staging tile (aliasing the idle P^T buffer) and one bulk
+//     tensor reduce-add (cp.reduce.async.bulk.tensor .add) per 32-column box, so the L2 atomics run
+//     asynchronously instead of stalling the softmax threads on per-lane red.global traffic;
+//   * reads LSE / delta as 128-bit shared loads, prefetched one iteration ahead.
+// smem: K 16 + V 16 + Q 2x16 + dO 2x16 + P^T 2x32 + dS^T 2x32 = 224 KB (+2 KB lse/delta + barriers).
+// TMEM: S^T 128 | dP^T 128 | dV 64 | dK 64 | dQ 64 columns.
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "host.h"
+
+namespace b200 {
+
+namespace {
+
+constexpr int B64_THREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2-9 two softmax warpgroups
+constexpr int BT = 128;
+constexpr int D = 64;
+constexpr int TILE = 128 * D * 2;       // 16 KB
+constexpr int PT_BYTES = 128 * 128 * 2;  // 32 KB
+constexpr int OFF_K = 0;
+constexpr int OFF_V = OFF_K + TILE;
+constexpr int OFF_Q = OFF_V + TILE;        // 2 stages
+constexpr int OFF_DO = OFF_Q + 2 * TILE;   // 2 stages
+constexpr int OFF_PT = OFF_DO + 2 * TILE;  // 2 buffers
+constexpr int OFF_DS = OFF_PT + 2 * PT_BYTES;
+constexpr int OFF_LSE = OFF_DS + 2 * PT_BYTES;  // [2 slots][lse 128 | delta 128] floats
+constexpr int OFF_BAR = OFF_LSE + 2 * 256 * 4;
+constexpr int SMEM_BYTES = OFF_BAR + 128;
+constexpr int TM_S = 0, TM_DP = 128, TM_DV = 256, TM_DK = 320, TM_DQ = 384;
+// dQ drain flavour: bulk tensor reduce-add (one instruction, asynchronous) vs coalesced red.global.v4.
+// Both are bound by L2 atomic throughput (~1 TB/s measured); the direct form measured 5 % faster.
+constexpr bool kTmaReduceDrain = false;
+
+struct Bwd64Args {
+  const float* lse;
+  const float* delta;
+  float* dq_acc;
+  __nv_bfloat16* dk;
+  __nv_bfloat16* dv;
+  int B, S, H, Hk;
+  float scale;
+  int causal;
+  long long* trace;  // debug: clock64 stamps of CTA (0,0,0), see tools/attn_trace.py
+};
+
+#define T64(slot)                                                                             \
+  do {                                                                                        \
+    if (p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && it < 16) \
+      p.trace[it * 16 + (slot)] = clock64();                                                  \
+  } while (0)
+
+__device__ __forceinline__ float ex2f(float x) {
+  float y;
+  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void red_add_v4(float* addr, float4 v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ void st_tile_chunk(uint32_t tile, int row, int chunk, const float* f) {
+  const uint32_t addr = tile + (chunk >> 3) * 16384 + row * 128 + (((chunk & 7) ^ (row & 7)) << 4);
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pack_bf16x2(f[0], f[1])),
+               "r"(pack_bf16x2(f[2], f[3])), "r"(pack_bf16x2(f[4], f[5])), "r"(pack_bf16x2(f[6], f[7]))
+               : "memory");
+}
+
+__global__ void __launch_bounds__(B64_THREADS, 1)
+attn_bwd64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                  const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
+                  const __grid_constant__ CUtensorMap tmDQ, const Bwd64Args p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t sbase = smem_u32(smem);
+  if ((sbase & 1023u) != 0) __trap();  // 128B-swizzled TMA/UMMA tiles need a 1 KB aligned base
+  const uint32_t sK = sbase + OFF_K, sV = sbase + OFF_V;
+  auto sQ = [&](int st) { return sbase + OFF_Q + st * TILE; };
+  auto sDO = [&](int st) { return sbase + OFF_DO + st * TILE; };
+  auto sPT = [&](int bf) { return sbase + OFF_PT + bf * PT_BYTES; };
+  auto sDS = [&](int bf) { return sbase + OFF_DS + bf * PT_BYTES; };
+  float* lse_s = reinterpret_cast<float*>(smem + OFF_LSE);
+  const uint32_t bar = sbase + OFF_BAR;
+  const uint32_t kv_full = bar;
+  auto q_full = [&](int s) { return bar + 8u * (1 + s); };
+  auto q_empty = [&](int s) { return bar + 8u * (3 + s); };
+  const uint32_t s_full = bar + 8u * 5;
+  const uint32_t pds_full = bar + 8u * 6;
+  const uint32_t dq_full = bar + 8u * 7;
+  const uint32_t dq_empty = bar + 8u * 8;
+  const uint32_t tmem_slot = bar + 8u * 9;
+
+  const int warp = warp_idx_uniform();
+  const int lane = threadIdx.x & 31;
+  const int kt = blockIdx.x, hk = blockIdx.y, b = blockIdx.z;
+  const int G = p.H / p.Hk;
+  const int k0 = kt * BT;
+  const int n_qt_all = (p.S + BT - 1) / BT;
+  const int qt_first = p.causal ? kt : 0;
+  const int n_qt = n_qt_all - qt_first;
+  const int n_it = G * n_qt;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    tma_prefetch_desc(&tmDO);
+    tma_prefetch_desc(&tmDQ);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(kv_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(q_full(s), 1);
+      mbar_init(q_empty(s), 1);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(pds_full, 8);
+    mbar_init(dq_full, 1);
+    mbar_init(dq_empty, 8);
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------------------------- TMA producer ------------------------------------
+      mbar_arrive_expect_tx(kv_full, 2 * TILE);
+      tma_load_4d(sK, &tmK, kv_full, 0, hk, k0, b);
+      tma_load_4d(sV, &tmV, kv_full, 0, hk, k0, b);
+      for (int it = 0; it < n_it; ++it) {
+        const int st = it & 1;
+        const uint32_t ph = (it >> 1) & 1u;
+        const int h = hk * G + it / n_qt;
+        const int q0 = (qt_first + it % n_qt) * BT;
+        mbar_wait(q_empty(st), ph ^ 1u);
+        mbar_arrive_expect_tx(q_full(st), 2 * TILE);
+        tma_load_4d(sQ(st), &tmQ, q_full(st), 0, h, q0, b);
+        tma_load_4d(sDO(st), &tmDO, q_full(st), 0, h, q0, b);
+      }
+    }
+  } else if (warp == 1) {
+    // ------- MMA issuer: uniform control flow on the whole warp, one elected lane issues --------
+    constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, false, false);  // K-major x K-major
+    constexpr uint32_t idesc_kv = make_idesc_bf16(128, D, false, true);    // K-major x MN-major
+    constexpr uint32_t idesc_dq = make_idesc_bf16(128, D, true, true);     // MN-major x MN-major
+    auto issue_s = [&](int it) {  // S^T = K Q^T, dP^T = V dO^T  (M = keys, N = queries, K = head dim)
+      const int st = it & 1;
+      mbar_wait(q_full(st), (it >> 1) & 1u);
+      tc_fence_after_sync();
+      if (elect_one()) {
+#pragma unroll
+        for (int kk = 0; kk < D / 16; ++kk)
+          umma_bf16_ss(tmem_base + TM_S, make_smem_desc_sw128(sK + kk * 32, 0, 1024),
+                       make_smem_desc_sw128(sQ(st) + kk * 32, 0, 1024), idesc_s, kk != 0);
+#pragma unroll
+        for (int kk = 0; kk < D / 16; ++kk)
+          umma_bf16_ss(tmem_base + TM_DP, make_smem_desc_sw128(sV + kk * 32, 0, 1024),
+                       make_smem_desc_sw128(sDO(st) + kk * 32, 0, 1024), idesc_s, kk != 0);
+        umma_commit(s_full);
+      }
+      __syncwarp();
+    };
+    mbar_wait(kv_full, 0);
+    if (n_it > 0) issue_s(0);
+    for (int it = 0; it < n_it; ++it) {
+      const int st = it & 1, bf = it & 1;
+      if (lane == 0) T64(8);
+      mbar_wait(pds_full, it & 1u);  // softmax(it) done: S/dP columns free, P^T/dS^T[bf] written
+      if (lane == 0) T64(9);
+      if (it + 1 < n_it) issue_s(it + 1);
+      if (lane == 0) T64(10);
+      if (it > 0) mbar_wait(dq_empty, (it - 1) & 1u);  // dQ(it-1) left TMEM
+      tc_fence_after_sync();
+      if (lane == 0) T64(11);
+      if (elect_one()) {
+        // dV += P^T dO ; dK += dS^T Q  (M = keys, N = head dim, K = queries)
+#pragma unroll
+        for (int kk = 0; kk < BT / 16; ++kk)
+          umma_bf16_ss(tmem_base + TM_DV, make_smem_desc_sw128(sPT(bf) + (kk >> 2) * 16384 + (kk & 3) * 32, 0, 1024),
+                       make_smem_desc_sw128(sDO(st) + kk * 2048, 16384, 1024), idesc_kv, (it | kk) != 0);
+#pragma unroll
+        for (int kk = 0; kk < BT / 16; ++kk)
+          umma_bf16_ss(tmem_base + TM_DK, make_smem_desc_sw128(sDS(bf) + (kk >> 2) * 16384 + (kk & 3) * 32, 0, 1024),
+                       make_smem_desc_sw128(sQ(st) + kk * 2048, 16384, 1024), idesc_kv, (it | kk) != 0);
+        // dQ = dS K  (M = queries, N = head dim, K = keys): dS^T tile read as an MN-major A operand
+#pragma unroll
+        for (int kk = 0; kk < BT / 16; ++kk)
+          umma_bf16_ss(tmem_base + TM_DQ, make_smem_desc_sw128(sDS(bf) + kk * 2048, 16384, 1024),
+                       make_smem_desc_sw128(sK + kk * 2048, 16384, 1024), idesc_dq, kk != 0);
+        umma_commit(q_empty(st));
+        umma_commit(dq_full);
+      }
+      __syncwarp();
+      if (lane == 0) T64(12);
+    }
+  } else {
+    // --------------------------- softmax / dQ drain / dK,dV epilogue ------------------------
+    const int qd = warp & 3;
+    const int wg = (warp - 2) >> 2;
+    const int row = qd * 32 + lane;  // key row (S^T) or query row (dQ)
+    const int key = k0 + row;
+    const uint32_t t_lane = tmem_base + (uint32_t(qd * 32) << 16);
+    const float sl2 = p.scale * 1.4426950408889634f;
+    const int tid = threadIdx.x - 64;  // 0..255
+    const int cbase = wg * 64;
+
+    // lse*log2e (threads 0-127) / delta (threads 128-255) of the 128 queries of iteration `it`:
+    // fetched into a register at the top of the previous iteration, parked in smem after its softmax
+    auto fetch_lse = [&](int it) -> float {
+      const int h = hk * G + it / n_qt;
+      const int q = (qt_first + it % n_qt) * BT + (tid & 127);
+      const long long idx = ((long long)b * p.H + h) * p.S + q;
+      const float* src = (tid < 128 ? p.lse : p.delta) + (q < p.S ? idx : 0);
+      float val;  // asm: keeps the compiler from scheduling the first use (and its stall) right here
+      asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(val) : "l"(src));
+      return val;
+    };
+    auto put_lse = [&](int it, float val) {
+      const int q = (qt_first + it % n_qt) * BT + (tid & 127);
+      if (tid < 128)
+        val = q < p.S ? val * 1.4426950408889634f : INFINITY;
+      else
+        val = q < p.S ? val : 0.f;
+      lse_s[(it & 1) * 256 + tid] = val;
+    };
+    // dQ(it): TMEM -> fp32 staging tile in TMA layout (two [128 x 128 B] 128B-swizzled boxes, aliasing
+    // P^T[it & 1], idle once dq_full(it) fired) -> ONE bulk tensor reduce-add per box into dq_acc.  The
+    // threads only pay for the staging; the L2 atomics run asynchronously behind the next softmax.
+    auto drain_dq = [&](int it) {
+      const int h = hk * G + it / n_qt;
+      const int q0 = (qt_first + it % n_qt) * BT;
+      mbar_wait(dq_full, it & 1u);
+      tc_fence_after_sync();
+      uint32_t v[32];
+      tmem_ld_32x32b_x32(t_lane + TM_DQ + wg * 32, v);
+      tmem_ld_wait();
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(dq_empty);
+      if constexpr (kTmaReduceDrain) {
+        const uint32_t stg = sPT(it & 1) + wg * 16384 + row * 128;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + ((j ^ (row & 7)) << 4)),
+                       "r"(v[j * 4 + 0]), "r"(v[j * 4 + 1]), "r"(v[j * 4 + 2]), "r"(v[j * 4 + 3])
+                       : "memory");
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(1, 256);
+        if (tid == 0) {
+          tma_reduce_add_4d(&tmDQ, sPT(it & 1), 0, h, q0, b);
+          tma_reduce_add_4d(&tmDQ, sPT(it & 1) + 16384, 32, h, q0, b);
+          tma_commit_group();
+          tma_wait_group_read<0>();  // staging tile may be overwritten once the bulk op has read it
+        }
+      } else {
+        // [128 rows][16 chunks of 16 B], chunk ^= row & 15; then coalesced red.global.add.v4.f32: every
+        // warp instruction covers two contiguous 256-byte rows (4 lines instead of 32)
+        const uint32_t stg = sPT(it & 1);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int ch = wg * 8 + j;
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + row * 256 + ((ch ^ (row & 15)) << 4)),
+                       "r"(v[j * 4 + 0]), "r"(v[j * 4 + 1]), "r"(v[j * 4 + 2]), "r"(v[j * 4 + 3])
+                       : "memory");
+        }
+        named_bar_sync(1, 256);
+        float* dst = p.dq_acc + (((long long)b * p.S + q0) * p.H + h) * D;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int c = tid + 256 * i;  // 16-byte chunk id: row = c / 16, chunk = c % 16
+          const int r = c >> 4, ch = c & 15;
+          float4 val;
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                       : "=f"(val.x), "=f"(val.y), "=f"(val.z), "=f"(val.w)
+                       : "r"(stg + r * 256 + ((ch ^ (r & 15)) << 4)));
+          if (q0 + r < p.S) red_add_v4(dst + (long long)r * p.H * D + ch * 4, val);
+        }
+      }
+    };
+
+    if (n_it > 0) put_lse(0, fetch_lse(0));
+    named_bar_sync(1, 256);
+    for (int it = 0; it < n_it; ++it) {
+      const int bf = it & 1;
+      const int q0 = (qt_first + it % n_qt) * BT;
+      const float* lse2 = lse_s + (it & 1) * 256;
+      const float* dlt = lse2 + 128;
+      const bool diag = p.causal && q0 == k0;  // tiles are aligned: only the diagonal tile is cut
+      if (threadIdx.x == 64) T64(0);
+      float lse_next = 0.f;
+      if (it + 1 < n_it) lse_next = fetch_lse(it + 1);  // latency hides behind this iteration's softmax
+      mbar_wait(s_full, it & 1u);
+      tc_fence_after_sync();
+      if (threadIdx.x == 64) T64(1);
+#pragma unroll 1
+      for (int c0 = cbase; c0 < cbase + 64; c0 += 32) {
+        uint32_t vs[32], vd[32];
+        tmem_ld_32x32b_x32(t_lane + TM_S + c0, vs);
+        tmem_ld_32x32b_x32(t_lane + TM_DP + c0, vd);
+        tmem_ld_wait();
+        float pr[32], ds[32];
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          const float4 l4 = *reinterpret_cast<const float4*>(lse2 + c0 + g * 4);
+          const float4 d4 = *reinterpret_cast<const float4*>(dlt + c0 + g * 4);
+          const float ls[4] = {l4.x, l4.y, l4.z, l4.w};
+          const float dl[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int qc = c0 + g * 4 + i;
+            float e = ex2f(fmaf(__uint_as_float(vs[g * 4 + i]), sl2, -ls[i]));
+            if ((diag && (q0 + qc < key)) || key >= p.S) e = 0.f;
+            pr[g * 4 + i] = e;
+            ds[g * 4 + i] = e * (__uint_as_float(vd[g * 4 + i]) - dl[i]) * p.scale;
+          }
+        }
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          st_tile_chunk(sPT(bf), row, (c0 >> 3) + g, pr + g * 8);
+          st_tile_chunk(sDS(bf), row, (c0 >> 3) + g, ds + g * 8);
+        }
+      }
+      tc_fence_before_sync();
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(pds_full);
+      if (threadIdx.x == 64) T64(2);
+
+      if (it + 1 < n_it) put_lse(it + 1, lse_next);  // visible after the barriers below, before softmax(it+1)
+      if (threadIdx.x == 64) T64(3);
+      if (it > 0) drain_dq(it - 1);          // tensor core is busy with dV,dK,dQ(it) meanwhile
+      if (threadIdx.x == 64) T64(4);
+      named_bar_sync(1, 256);                // staging reads done before P^T[(it-1)&1] is rewritten
+      if (threadIdx.x == 64) T64(5);
+    }
+    if (n_it > 0) {
+      drain_dq(n_it - 1);
+      if (tid == 0) tma_wait_group<0>();  // all reduce-adds of this CTA have landed in dq_acc
+      named_bar_sync(1, 256);
+    }
+
+    // dK / dV (the last dq_full commit covers every MMA issued before it); column halves per warpgroup
+#pragma unroll 1
+    for (int which = 0; which < 2; ++which) {
+      __nv_bfloat16* out = (which == 0 ? p.dv : p.dk) + (((long long)b * p.S + key) * p.Hk + hk) * D + wg * 32;
+      uint32_t v[32];
+      tmem_ld_32x32b_x32(t_lane + (which == 0 ? TM_DV : TM_DK) + wg * 32, v);
+      tmem_ld_wait();
+      if (key < p.S) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 o4;
+          o4.x = pack_bf16x2(__uint_as_float(v[g * 8 + 0]), __uint_as_float(v[g * 8 + 1]));
+          o4.y = pack_bf16x2(__uint_as_float(v[g * 8 + 2]), __uint_as_float(v[g * 8 + 3]));
+          o4.z = pack_bf16x2(__uint_as_float(v[g * 8 + 4]), __uint_as_float(v[g * 8 + 5]));
+          o4.w = pack_bf16x2(__uint_as_float(v[g * 8 + 6]), __uint_as_float(v[g * 8 + 7]));
+          stg128(out + g * 8, o4);
+        }
+      }
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace
+
+int make_bshd_map(CUtensorMap* tm, const void* base, int B, int S, int heads, int D, int box_rows, bool f32);
+
+int launch_attn_bwd64(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV,
+                      const CUtensorMap& tmDO, const float* lse, const float* delta, float* dq_acc, void* dk,
+                      void* dv, int B, int S, int H, int Hk, float scale, int causal, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    B200_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    attr_set = true;
+  }
+  Bwd64Args a;
+  a.lse = lse;
+  a.delta = delta;
+  a.dq_acc = dq_acc;
+  a.dk = reinterpret_cast<__nv_bfloat16*>(dk);
+  a.dv = reinterpret_cast<__nv_bfloat16*>(dv);
+  a.B = B;
+  a.S = S;
+  a.H = H;
+  a.Hk = Hk;
+  a.scale = scale;
+  a.causal = causal;
+  {
+    const char* e = getenv("B200_ATTN_TRACE");
+    a.trace = e ? reinterpret_cast<long long*>(strtoull(e, nullptr, 16)) : nullptr;
+  }
+  CUtensorMap tmDQ;  // fp32 [B,S,H,64] accumulator, box {32, 1, 128, 1}
+  if (int rc = make_bshd_map(&tmDQ, dq_acc, B, S, H, D, BT, true)) return rc;
+  dim3 grid((S + BT - 1) / BT, Hk, B);
+  attn_bwd64_kernel<<<grid, B64_THREADS, SMEM_BYTES, stream>>>(tmQ, tmK, tmV, tmDO, tmDQ, a);
+  B200_CHECK_LAUNCH();
+  return B200_OK;
+}
+
+}  // namespace b200

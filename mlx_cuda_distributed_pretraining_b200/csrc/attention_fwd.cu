@@ -79,7 +79,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const uint32_t tmem_slot = bar + 8u * 15;
   float* red_s = reinterpret_cast<float*>(smem_raw + (sbase - smem_u32(smem_raw)) + Cfg::OFF_RED);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = warp_idx_uniform();
   const int lane = threadIdx.x & 31;
 
   const int qt = (int)gridDim.x - 1 - (int)blockIdx.x;  // heaviest (longest causal row) tiles first
@@ -138,8 +138,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ---------------------------------- MMA issuer --------------------------------------
+    {
+      // ------ MMA issuer: whole warp runs the uniform control flow, one elected lane issues ------
       constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, false, false);
       constexpr uint32_t idesc_pv = make_idesc_bf16(128, D, false, true);
       auto issue_s = [&](int j) {
@@ -149,14 +149,17 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         mbar_wait(k_full(st), ph);
         tc_fence_after_sync();
         const uint32_t d_tmem = tmem_base + (sb ? Cfg::TM_S1 : Cfg::TM_S0);
+        if (elect_one()) {
 #pragma unroll
-        for (int kk = 0; kk < D / 16; ++kk) {
-          const uint32_t off = (kk >> 2) * 16384 + (kk & 3) * 32;
-          umma_bf16_ss(d_tmem, make_smem_desc_sw128(sQ + off, 0, 1024),
-                       make_smem_desc_sw128(sK(st) + off, 0, 1024), idesc_s, kk != 0);
+          for (int kk = 0; kk < D / 16; ++kk) {
+            const uint32_t off = (kk >> 2) * 16384 + (kk & 3) * 32;
+            umma_bf16_ss(d_tmem, make_smem_desc_sw128(sQ + off, 0, 1024),
+                         make_smem_desc_sw128(sK(st) + off, 0, 1024), idesc_s, kk != 0);
+          }
+          umma_commit(k_empty(st));
+          umma_commit(s_full(sb));
         }
-        umma_commit(k_empty(st));
-        umma_commit(s_full(sb));
+        __syncwarp();
       };
       mbar_wait(q_full, 0);
       issue_s(0);
@@ -166,14 +169,17 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         mbar_wait(p_full, j & 1u);
         mbar_wait(v_full(st), (j >> 1) & 1u);
         tc_fence_after_sync();
+        if (elect_one()) {
 #pragma unroll
-        for (int kk = 0; kk < ATT_BKV / 16; ++kk) {
-          const uint64_t da = make_smem_desc_sw128(sP + (kk >> 2) * 16384 + (kk & 3) * 32, 0, 1024);
-          const uint64_t db = make_smem_desc_sw128(sV(st) + kk * 2048, 16384, 1024);
-          umma_bf16_ss(tmem_base + Cfg::TM_O, da, db, idesc_pv, (j | kk) != 0);
+          for (int kk = 0; kk < ATT_BKV / 16; ++kk) {
+            const uint64_t da = make_smem_desc_sw128(sP + (kk >> 2) * 16384 + (kk & 3) * 32, 0, 1024);
+            const uint64_t db = make_smem_desc_sw128(sV(st) + kk * 2048, 16384, 1024);
+            umma_bf16_ss(tmem_base + Cfg::TM_O, da, db, idesc_pv, (j | kk) != 0);
+          }
+          umma_commit(v_empty(st));
+          umma_commit(pv_done);
         }
-        umma_commit(v_empty(st));
-        umma_commit(pv_done);
+        __syncwarp();
       }
     }
   } else {

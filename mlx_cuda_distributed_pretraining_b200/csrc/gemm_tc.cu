@@ -81,7 +81,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA,
   auto smem_a = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES; };
   auto smem_b = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES + A_STAGE_BYTES; };
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = warp_idx_uniform();
   const int lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
@@ -147,8 +147,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA,
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ------------------------------- MMA issuer ---------------------------------------
+    {
+      // ------ MMA issuer: whole warp runs the uniform control flow, one elected lane issues ------
       constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MN, B_MN);
       int stage = 0;
       uint32_t phase = 0;
@@ -164,23 +164,27 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA,
           tc_fence_after_sync();
           const uint32_t a_addr = smem_a(stage);
           const uint32_t b_addr = smem_b(stage);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            // K-major: advance 16 elements = 32 B inside the 128 B swizzle row.
-            // MN-major: advance 16 k-rows = 2 swizzle atoms of 1024 B.
-            const uint64_t da = A_MN ? make_smem_desc_sw128(a_addr + k * 2048, 8192, 1024)
-                                     : make_smem_desc_sw128(a_addr + k * 32, 0, 1024);
-            const uint64_t db = B_MN ? make_smem_desc_sw128(b_addr + k * 2048, 8192, 1024)
-                                     : make_smem_desc_sw128(b_addr + k * 32, 0, 1024);
-            umma_bf16_ss(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              // K-major: advance 16 elements = 32 B inside the 128 B swizzle row.
+              // MN-major: advance 16 k-rows = 2 swizzle atoms of 1024 B.
+              const uint64_t da = A_MN ? make_smem_desc_sw128(a_addr + k * 2048, 8192, 1024)
+                                       : make_smem_desc_sw128(a_addr + k * 32, 0, 1024);
+              const uint64_t db = B_MN ? make_smem_desc_sw128(b_addr + k * 2048, 8192, 1024)
+                                       : make_smem_desc_sw128(b_addr + k * 32, 0, 1024);
+              umma_bf16_ss(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+            umma_commit(empty_bar(stage));  // frees the smem slot once these MMAs retire
           }
-          umma_commit(empty_bar(stage));  // frees the smem slot once these MMAs retire
+          __syncwarp();
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1u;
           }
         }
-        umma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+        if (elect_one()) umma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+        __syncwarp();
       }
     }
   } else if (warp >= 4) {

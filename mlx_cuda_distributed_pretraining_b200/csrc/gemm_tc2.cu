@@ -134,7 +134,7 @@ gemm2_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   auto smem_a = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES; };
   auto smem_b = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES + G2_A_BYTES; };
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = warp_idx_uniform();
   const int lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
@@ -209,8 +209,9 @@ gemm2_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && leader) {
-      // ------------------------- MMA issuer (leader only) -----------------------------------
+    if (leader) {
+      // ------------- MMA issuer (leader only): the whole warp runs the (uniform) control flow, -----
+      // ------------- one elected lane issues, so descriptors stay on the uniform datapath ---------
       constexpr uint32_t idesc = make_idesc_bf16(256, BN, A_MN, B_MN);
       int stage = 0;
       uint32_t phase = 0;
@@ -226,21 +227,25 @@ gemm2_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           tc_fence_after_sync();
           const uint32_t a_addr = smem_a(stage);
           const uint32_t b_addr = smem_b(stage);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < G2_BK / 16; ++k) {
-            const uint64_t da = A_MN ? make_smem_desc_sw128(a_addr + k * 2048, 8192, 1024)
-                                     : make_smem_desc_sw128(a_addr + k * 32, 0, 1024);
-            const uint64_t db = B_MN ? make_smem_desc_sw128(b_addr + k * 2048, 8192, 1024)
-                                     : make_smem_desc_sw128(b_addr + k * 32, 0, 1024);
-            umma2_bf16_ss(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < G2_BK / 16; ++k) {
+              const uint64_t da = A_MN ? make_smem_desc_sw128(a_addr + k * 2048, 8192, 1024)
+                                       : make_smem_desc_sw128(a_addr + k * 32, 0, 1024);
+              const uint64_t db = B_MN ? make_smem_desc_sw128(b_addr + k * 2048, 8192, 1024)
+                                       : make_smem_desc_sw128(b_addr + k * 32, 0, 1024);
+              umma2_bf16_ss(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+            umma2_commit_mc(empty_bar(stage));
           }
-          umma2_commit_mc(empty_bar(stage));
+          __syncwarp();
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1u;
           }
         }
-        umma2_commit_mc(tfull_bar(acc));
+        if (elect_one()) umma2_commit_mc(tfull_bar(acc));
+        __syncwarp();
       }
     }
   } else if (warp >= 4) {
