@@ -19,7 +19,8 @@ namespace b200 {
 
 namespace {
 
-constexpr int G2_THREADS = 256;
+constexpr int G2_EPI_WARPS = 8;  // two warps per TMEM lane quarter, each owning half of the tile's columns
+constexpr int G2_THREADS = 128 + 32 * G2_EPI_WARPS;
 constexpr int G2_BK = 64;
 constexpr int G2_A_BYTES = 128 * G2_BK * 2;  // 16 KB per CTA per stage
 
@@ -34,6 +35,8 @@ struct Gemm2Args {
   void* D;
   long long ldd, strideD;
   int symmetric;  // D is symmetric (M == N, BN == 256): compute tiles with mi <= ni, mirror-write the rest
+  int k_splits;   // > 1: every tile's K range is cut into k_splits work items, each storing its raw fp32
+  float* ws;      //      partial into slab ws[split][batch][M][N]; splitk_finalize_kernel applies the epilogue
 };
 
 // tile index -> (mi, ni).  Symmetric mode walks the upper triangle row by row.
@@ -153,7 +156,7 @@ gemm2_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);   // multicast commit
-      mbar_init(tempty_bar(a), 8);  // 4 epilogue warps x 2 CTAs (leader only)
+      mbar_init(tempty_bar(a), 2 * G2_EPI_WARPS);  // epilogue warps x 2 CTAs (leader only)
     }
     fence_mbar_init();
   }
@@ -165,22 +168,33 @@ gemm2_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
+  // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch)
+  // may overlap the tail of the previous kernel in the stream; nothing below may, because operands and
+  // C/D belong to the chain.  Our own dependents are released right away - they block in the same wait.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+
   const int tiles_per_batch = p.symmetric ? p.tiles_m * (p.tiles_m + 1) / 2 : p.tiles_m * p.tiles_n;
   const int total_tiles = tiles_per_batch * p.batch;
   const int num_kb = (p.K + G2_BK - 1) / G2_BK;
+  const int total_work = total_tiles * p.k_splits;  // work item w -> (tile w / k_splits, split w % k_splits)
 
   if (warp == 0) {
     if (lane == 0) {
       // ------------------------- TMA producer (both CTAs) -----------------------------------
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
+      for (int w = cluster_id; w < total_work; w += num_clusters) {
+        const int tile = w / p.k_splits;
+        const int split = w - tile * p.k_splits;
+        const int kb_begin = (int)((long long)split * num_kb / p.k_splits);
+        const int kb_end = (int)((long long)(split + 1) * num_kb / p.k_splits);
         const int b = tile / tiles_per_batch;
         int mi, ni;
         tile_coords(p, tile - b * tiles_per_batch, mi, ni);
         const int m0 = mi * 256 + (int)rank * 128;
         const int n0 = ni * BN + (int)rank * BNH;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const int k0 = kb * G2_BK;
           if constexpr (!A_MN) {
@@ -216,13 +230,16 @@ gemm2_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       int stage = 0;
       uint32_t phase = 0;
       uint32_t iter = 0;
-      for (int tile = cluster_id; tile < total_tiles; tile += num_clusters, ++iter) {
+      for (int w = cluster_id; w < total_work; w += num_clusters, ++iter) {
+        const int split = w % p.k_splits;
+        const int kb_begin = (int)((long long)split * num_kb / p.k_splits);
+        const int kb_end = (int)((long long)(split + 1) * num_kb / p.k_splits);
         const uint32_t acc = iter & 1u;
         const uint32_t acc_phase = (iter >> 1) & 1u;
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after_sync();
         const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after_sync();
           const uint32_t a_addr = smem_a(stage);
@@ -234,7 +251,7 @@ gemm2_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                                        : make_smem_desc_sw128(a_addr + k * 32, 0, 1024);
               const uint64_t db = B_MN ? make_smem_desc_sw128(b_addr + k * 2048, 8192, 1024)
                                        : make_smem_desc_sw128(b_addr + k * 32, 0, 1024);
-              umma2_bf16_ss(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+              umma2_bf16_ss(d_tmem, da, db, idesc, (kb != kb_begin || k != 0) ? 1u : 0u);
             }
             umma2_commit_mc(empty_bar(stage));
           }
@@ -251,11 +268,15 @@ gemm2_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   } else if (warp >= 4) {
     // ------------------------------- epilogue (both CTAs) -----------------------------------
     constexpr int VEC = (sizeof(OutT) == 2) ? 8 : 4;
-    constexpr int NCV = BN / VEC;  // 16-byte C vectors per row
-    const int q = warp - 4;
+    constexpr int BNW = BN / (G2_EPI_WARPS / 4);  // columns per epilogue warp
+    constexpr int NCV = BNW / VEC;                // 16-byte C vectors per row and warp
+    const int q = warp & 3;
+    const int cbase = ((warp - 4) >> 2) * BNW;
     const int row = q * 32 + lane;
     uint32_t iter = 0;
-    for (int tile = cluster_id; tile < total_tiles; tile += num_clusters, ++iter) {
+    for (int w = cluster_id; w < total_work; w += num_clusters, ++iter) {
+      const int tile = w / p.k_splits;
+      const int split = w - tile * p.k_splits;
       const int b = tile / tiles_per_batch;
       int mi, ni;
       tile_coords(p, tile - b * tiles_per_batch, mi, ni);
@@ -264,6 +285,34 @@ gemm2_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       const bool mirror = p.symmetric && mi != ni;
       const uint32_t acc = iter & 1u;
       const uint32_t acc_phase = (iter >> 1) & 1u;
+      if (p.k_splits > 1) {
+        // split-K: raw fp32 partial into this split's slab; alpha/beta/C/mirroring happen in the finalize
+        const int gm_ = m0 + row;
+        float* wrow = p.ws + (((long long)split * p.batch + b) * p.M + gm_) * (long long)p.N;
+        mbar_wait(tfull_bar(acc), acc_phase);
+        tc_fence_after_sync();
+        const uint32_t t_row_ = tmem_base + (uint32_t(q * 32) << 16) + acc * BN;
+#pragma unroll 2
+        for (int c0 = cbase; c0 < cbase + BNW; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(t_row_ + c0, v);
+          tmem_ld_wait();
+          if (gm_ < p.M) {
+#pragma unroll
+            for (int g = 0; g < 32; g += 4) {
+              const int gn = n0 + c0 + g;
+              if (gn < p.N)
+                *reinterpret_cast<float4*>(wrow + gn) =
+                    make_float4(__uint_as_float(v[g]), __uint_as_float(v[g + 1]), __uint_as_float(v[g + 2]),
+                                __uint_as_float(v[g + 3]));
+            }
+          }
+        }
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(tempty_bar(acc), 0);
+        continue;
+      }
       const float alpha = p.alpha * (p.alpha_vec ? p.alpha_vec[b] : 1.0f);
       const float beta = p.beta * (p.beta_vec ? p.beta_vec[b] : 1.0f);
       const int gm = m0 + row;
@@ -279,7 +328,7 @@ gemm2_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         if (crow && row_ok) {
 #pragma unroll
           for (int i = 0; i < NCV; ++i)
-            cpre[i] = (n0 + i * 8 < p.N) ? ldg128(crow + n0 + i * 8) : make_uint4(0, 0, 0, 0);
+            cpre[i] = (n0 + cbase + i * 8 < p.N) ? ldg128(crow + n0 + cbase + i * 8) : make_uint4(0, 0, 0, 0);
         }
       }
 
@@ -287,7 +336,8 @@ gemm2_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       tc_fence_after_sync();
       const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + acc * BN;
 #pragma unroll
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      for (int cc = 0; cc < BNW; cc += 32) {
+        const int c0 = cbase + cc;
         uint32_t v[32];
         tmem_ld_32x32b_x32(t_row + c0, v);
         tmem_ld_wait();
@@ -301,7 +351,7 @@ gemm2_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
               for (int i = 0; i < VEC; ++i) f[i] = alpha * __uint_as_float(v[g + i]);
               if constexpr (VEC == 8) {
                 if (crow) {
-                  const uint4 cv = cpre[(c0 + g) / 8];
+                  const uint4 cv = cpre[(cc + g) / 8];
                   const float2 c01 = unpack_bf16x2(cv.x), c23 = unpack_bf16x2(cv.y),
                                c45 = unpack_bf16x2(cv.z), c67 = unpack_bf16x2(cv.w);
                   f[0] = fmaf(beta, c01.x, f[0]);
@@ -359,6 +409,45 @@ gemm2_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   }
 }
 
+// Split-K epilogue: D = bf16(alpha * sum_s ws[s]) in a fixed summation order (deterministic), with the
+// symmetric mode's mirror writes.  Lanes own consecutive rows, as in the GEMM epilogue, so the mirrored
+// 2-byte stores of one instruction fill a contiguous 64-byte run.
+__global__ void __launch_bounds__(256)
+splitk_finalize_kernel(const float* __restrict__ ws, int splits, int batch, int M, int N, __nv_bfloat16* D,
+                       long long ldd, long long strideD, float alpha, const float* __restrict__ alpha_vec,
+                       int symmetric) {
+  const int b = blockIdx.z;
+  const int i = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int j0 = (blockIdx.y * 8 + (threadIdx.x >> 5)) * 8;
+  if (i >= M || j0 >= N) return;
+  const int ti = i >> 8, tj = j0 >> 8;
+  if (symmetric && ti > tj) return;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int s = 0; s < splits; ++s) {
+    const float* src = ws + (((long long)s * batch + b) * M + i) * (long long)N + j0;
+    const float4 v0 = *reinterpret_cast<const float4*>(src);
+    const float4 v1 = *reinterpret_cast<const float4*>(src + 4);
+    acc[0] += v0.x; acc[1] += v0.y; acc[2] += v0.z; acc[3] += v0.w;
+    acc[4] += v1.x; acc[5] += v1.y; acc[6] += v1.z; acc[7] += v1.w;
+  }
+  const float a = alpha * (alpha_vec ? alpha_vec[b] : 1.0f);
+  uint4 o;
+  o.x = pack_bf16x2(a * acc[0], a * acc[1]);
+  o.y = pack_bf16x2(a * acc[2], a * acc[3]);
+  o.z = pack_bf16x2(a * acc[4], a * acc[5]);
+  o.w = pack_bf16x2(a * acc[6], a * acc[7]);
+  __nv_bfloat16* dbase = D + (long long)b * strideD;
+  stg128(dbase + (long long)i * ldd + j0, o);
+  if (symmetric && ti != tj) {
+    const uint32_t w[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const uint16_t h = (t & 1) ? (uint16_t)(w[t >> 1] >> 16) : (uint16_t)(w[t >> 1] & 0xffffu);
+      *reinterpret_cast<uint16_t*>(dbase + (long long)(j0 + t) * ldd + i) = h;
+    }
+  }
+}
+
 template <bool A_MN, bool B_MN, typename OutT, int BN>
 int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gemm2Args& args, cudaStream_t stream) {
   using Cfg = G2Cfg<BN>;
@@ -369,10 +458,24 @@ int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gemm2Args
     attr_set = true;
   }
   const int total = (args.symmetric ? args.tiles_m * (args.tiles_m + 1) / 2 : args.tiles_m * args.tiles_n) *
-                    args.batch;
+                    args.batch * args.k_splits;
   const int pairs = num_sms() / 2;
   const int clusters = total < pairs ? total : pairs;
-  kern<<<2 * clusters, G2_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, args);
+  static const bool use_pdl = [] {
+    const char* e = getenv("B200_GEMM_PDL");
+    return !(e != nullptr && e[0] == '0');
+  }();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * clusters);
+  cfg.blockDim = dim3(G2_THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = use_pdl ? 1 : 0;
+  B200_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, args));
   B200_CHECK_LAUNCH();
   return B200_OK;
 }
@@ -394,8 +497,11 @@ int gemm_bf16_2cta(bool a_mn, bool b_mn, int M, int N, int K, int batch, const v
                    long long strideA, const void* B, long long ldb, long long strideB, const void* C,
                    long long ldc, long long strideC, void* D, long long ldd, long long strideD, bool out_f32,
                    float alpha, float beta, const float* alpha_vec, const float* beta_vec, int bn,
-                   int symmetric, cudaStream_t stream) {
+                   int symmetric, int k_splits, float* splitk_ws, cudaStream_t stream) {
   if (symmetric && (M != N || bn != 256 || out_f32)) symmetric = 0;  // square bf16 256-tiles only
+  // split-K needs a plain alpha-only bf16 epilogue and 16-byte partial rows
+  if (k_splits > 1 && (!splitk_ws || out_f32 || beta != 0.0f || (N & 7) != 0)) k_splits = 1;
+  if (k_splits < 1) k_splits = 1;
   CUtensorMap tmA, tmB;
   {
     const uint64_t dims[3] = {(uint64_t)(a_mn ? M : K), (uint64_t)(a_mn ? K : M), (uint64_t)batch};
@@ -429,10 +535,20 @@ int gemm_bf16_2cta(bool a_mn, bool b_mn, int M, int N, int K, int batch, const v
   a.ldd = ldd;
   a.strideD = strideD;
   a.symmetric = symmetric;
-  if (!a_mn && !b_mn) return dispatch2<false, false>(out_f32, bn, tmA, tmB, a, stream);
-  if (!a_mn && b_mn) return dispatch2<false, true>(out_f32, bn, tmA, tmB, a, stream);
-  if (a_mn && b_mn) return dispatch2<true, true>(out_f32, bn, tmA, tmB, a, stream);
-  return dispatch2<true, false>(out_f32, bn, tmA, tmB, a, stream);
+  a.k_splits = k_splits;
+  a.ws = splitk_ws;
+  int rc;
+  if (!a_mn && !b_mn) rc = dispatch2<false, false>(out_f32, bn, tmA, tmB, a, stream);
+  else if (!a_mn && b_mn) rc = dispatch2<false, true>(out_f32, bn, tmA, tmB, a, stream);
+  else if (a_mn && b_mn) rc = dispatch2<true, true>(out_f32, bn, tmA, tmB, a, stream);
+  else rc = dispatch2<true, false>(out_f32, bn, tmA, tmB, a, stream);
+  if (rc || k_splits == 1) return rc;
+  const dim3 grid((M + 31) / 32, (N + 63) / 64, batch);
+  splitk_finalize_kernel<<<grid, 256, 0, stream>>>(splitk_ws, k_splits, batch, M, N,
+                                                   reinterpret_cast<__nv_bfloat16*>(D), ldd, strideD, alpha,
+                                                   alpha_vec, symmetric);
+  B200_CHECK_LAUNCH();
+  return B200_OK;
 }
 
 }  // namespace b200

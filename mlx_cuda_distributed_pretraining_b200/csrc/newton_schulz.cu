@@ -18,7 +18,27 @@ int gemm_bf16(bool a_mn, bool b_mn, int M, int N, int K, int batch, const void* 
               bool out_f32, float alpha, float beta, const float* alpha_vec, const float* beta_vec,
               int force_bn, cudaStream_t stream);
 
+int gemm_bf16_2cta(bool a_mn, bool b_mn, int M, int N, int K, int batch, const void* A, long long lda,
+                   long long strideA, const void* B, long long ldb, long long strideB, const void* C,
+                   long long ldc, long long strideC, void* D, long long ldd, long long strideD, bool out_f32,
+                   float alpha, float beta, const float* alpha_vec, const float* beta_vec, int bn,
+                   int symmetric, int k_splits, float* splitk_ws, cudaStream_t stream);
+
 static inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
+
+// G1 of a lone big matrix (the 32003 x 1024 embedding: 10 symmetric tiles, K = 32003) would occupy a
+// fraction of the CTA pairs for hundreds of microseconds.  Cut K so that every pair gets a work item.
+static int g1_k_splits(int batch, int m, int k) {
+  if (m <= 128 || (m & 7) != 0) return 1;
+  const int t = (m + 255) / 256;
+  const long long tiles = (long long)t * (t + 1) / 2 * batch;
+  const int pairs = num_sms() / 2;
+  if (tiles * 2 > pairs) return 1;
+  const int num_kb = (k + 63) / 64;
+  int s = (int)(pairs / tiles);
+  if (s > num_kb / 16) s = num_kb / 16;
+  return s < 2 ? 1 : s;
+}
 
 // A = X X^T and B = bA + cAA are symmetric: only tiles on or above the diagonal are computed and
 // the rest mirror-written (force_bn code understood by gemm_bf16; ignored when it cannot apply)
@@ -28,6 +48,8 @@ size_t newton_schulz_workspace_bytes(int batch, int rows, int cols, int steps) {
   const size_t m = rows < cols ? rows : cols;
   size_t bytes = 2 * align256((size_t)batch * m * m * 2);
   if (steps >= 2) bytes += align256((size_t)batch * rows * cols * 2);
+  const int splits = g1_k_splits(batch, (int)m, rows < cols ? cols : rows);
+  if (splits > 1) bytes += align256((size_t)splits * batch * m * m * 4);
   return bytes;
 }
 
@@ -53,6 +75,9 @@ int newton_schulz(const void* x_in, void* x_out, int batch, int rows, int cols, 
   void* Abuf = w;
   void* Bbuf = w + align256((size_t)batch * mm * 2);
   void* Xtmp = w + 2 * align256((size_t)batch * mm * 2);
+  const int splits = g1_k_splits(batch, m, tall ? rows : cols);
+  float* splitk_ws = reinterpret_cast<float*>(
+      w + 2 * align256((size_t)batch * mm * 2) + (steps >= 2 ? align256((size_t)batch * rc * 2) : 0));
 
   const void* cur = x_in;
   for (int it = 0; it < steps; ++it) {
@@ -61,7 +86,11 @@ int newton_schulz(const void* x_in, void* x_out, int batch, int rows, int cols, 
     const float* s2 = (it == 0) ? inv_norm_sq : nullptr;
     int rc_;
     // G1
-    if (!tall)
+    if (splits > 1)
+      rc_ = gemm_bf16_2cta(tall, tall, m, m, tall ? rows : cols, batch, cur, cols, rc, cur, cols, rc, nullptr,
+                           0, 0, Abuf, m, mm, false, 1.0f, 0.0f, s2, nullptr, 256, 1, splits, splitk_ws,
+                           stream);
+    else if (!tall)
       rc_ = gemm_bf16(false, false, m, m, cols, batch, cur, cols, rc, cur, cols, rc, nullptr, 0, 0,
                       Abuf, m, mm, false, 1.0f, 0.0f, s2, nullptr, kSym, stream);
     else

@@ -87,7 +87,8 @@ def test_newton_schulz_golden(ops, golden):
 
 
 @pytest.mark.parametrize("shape", [(2, 256, 512), (2, 512, 256), (1, 1024, 1024), (3, 512, 1024), (1, 2816, 1024),
-                                   (1, 1024, 2816), (1, 1000, 256), (1, 136, 72), (1, 32003, 1024)])
+                                   (1, 1024, 2816), (1, 1000, 256), (1, 136, 72), (1, 32003, 1024),
+                                   (1, 5000, 512), (1, 384, 9000)])   # last three: split-K G1
 def test_newton_schulz_vs_oracle(ops, shape):
     torch.manual_seed(1)
     g = torch.randn(*shape) * 0.02
