@@ -146,13 +146,14 @@ def load_peaks() -> dict:
 # ------------------------------------------------------------------------------------------------
 # CPU baseline: the oracle port of the reference step on the host cores (bounded sample)
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_step(sample_seqs: int = 2, ns_matrix_stride: int = 4) -> dict:
+def cpu_reference_step(sample_seqs: int = 4, ns_matrix_stride: int = 2) -> dict:
     """Times the CPU restatement of the reference step (oracle/reference_math.py, fp32) on the C2
     workload with a bounded sample: fwd+bwd on `sample_seqs` of the 16 sequences (extrapolated
     linearly in sequences) + the Muon update on every `ns_matrix_stride`-th transformer matrix and
     the embedding (extrapolated by Newton-Schulz flops)."""
     from oracle import reference_math as R
-    cores = os.cpu_count() or 1
+    # more than ~32 threads only adds oversubscription at these matrix sizes and blows the time bound
+    cores = min(os.cpu_count() or 1, 32)
     torch.set_num_threads(cores)
     c = C2
     d = R.LlamaDims(c["hidden"], c["inter"], c["layers"], c["heads"], c["kv_heads"], c["head_dim"],
@@ -192,7 +193,7 @@ def run_reference(args) -> None:
     for _ in range(max(args.warmup, 0) and 1):
         cpu_reference_step(1, 12)
     for _ in range(max(min(args.steps, 3), 1)):
-        last = cpu_reference_step(2, 4)
+        last = cpu_reference_step(4, 2)
         vals.append(last["value"])
     v = statistics.median(vals)
     c = C2
@@ -343,7 +344,7 @@ def main() -> None:
     }
     if world == 1 and not args.no_cpu_baseline:
         try:
-            line["cpu_baseline"] = cpu_reference_step(2, 4)
+            line["cpu_baseline"] = cpu_reference_step(4, 2)
         except Exception as e:  # noqa: BLE001
             line["cpu_baseline"] = {"error": repr(e)}
     print(json.dumps(line), flush=True)

@@ -118,6 +118,15 @@ size_t b200_rmsnorm_bwd_workspace_bytes(int rows, int H);   /* per-CTA dW partia
 int b200_rmsnorm_bwd(const void* dy, const void* x, const void* w, const float* rstd, void* dx,
                      float* dw_f32, int rows, int H, int is_bf16, void* workspace,
                      size_t workspace_bytes, void* stream);
+/* Residual add fused with the norm that follows it (arch/llama.py:316-319: h = x + sublayer(...), then
+ * the next norm reads h):  sum_out = x + delta (rounded to the storage type), y = rmsnorm(sum_out) * w.
+ * Backward: dx = dres + rmsnorm_bwd(dy) where dres (nullable) is the gradient that reached sum_out
+ * directly; dx is the gradient of both x and delta.  Same workspace as b200_rmsnorm_bwd. */
+int b200_add_rmsnorm_fwd(const void* x, const void* delta, const void* w, void* sum_out, void* y,
+                         float* rstd, int rows, int H, float eps, int is_bf16, void* stream);
+int b200_add_rmsnorm_bwd(const void* dy, const void* dres, const void* x, const void* w,
+                         const float* rstd, void* dx, float* dw_f32, int rows, int H, int is_bf16,
+                         void* workspace, size_t workspace_bytes, void* stream);
 /* x,y: [B,S,NH,D]; cos_t,sin_t: f32 [S,D/2]; backward=1 applies the inverse rotation */
 int b200_rope(const void* x, void* y, const float* cos_t, const float* sin_t, int B, int S, int NH,
               int D, int backward, int is_bf16, void* stream);

@@ -64,12 +64,17 @@ class FlashAttention(nn.Module):
 
     def forward(self, x: torch.Tensor, mask=None) -> torch.Tensor:
         B, S, _ = x.shape
-        q = self.q_proj(x).reshape(B, S, self.num_heads, self.head_dim)
-        k = self.k_proj(x).reshape(B, S, self.num_kv_heads, self.head_dim)
-        v = self.v_proj(x).reshape(B, S, self.num_kv_heads, self.head_dim)
+        if self.q_proj.bias is None and self.k_proj.bias is None and self.v_proj.bias is None:
+            q, k, v = ops.multi_linear(x, (self.q_proj.weight, self.k_proj.weight, self.v_proj.weight))
+        else:
+            q, k, v = self.q_proj(x), self.k_proj(x), self.v_proj(x)
+        q = q.reshape(B, S, self.num_heads, self.head_dim)
+        k = k.reshape(B, S, self.num_kv_heads, self.head_dim)
+        v = v.reshape(B, S, self.num_kv_heads, self.head_dim)
         if self.rope_tables is not None:
             cos_t, sin_t = self.rope_tables
             q = ops.rope(q, cos_t[:S], sin_t[:S])
             k = ops.rope(k, cos_t[:S], sin_t[:S])
         ctx = self._flash_attention(q, k, v, mask)
-        return self.o_proj(ctx.reshape(B, S, self.num_heads * self.head_dim))
+        ctx = ctx.reshape(B, S, self.num_heads * self.head_dim)
+        return ops.linear(ctx, self.o_proj.weight) if self.o_proj.bias is None else self.o_proj(ctx)

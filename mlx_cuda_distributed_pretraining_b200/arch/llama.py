@@ -71,7 +71,10 @@ class MLP(nn.Module):
         self.down_proj = nn.Linear(intermediate_size, hidden_size, bias=use_bias)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        return self.down_proj(ops.glu(self.gate_proj(x), self.up_proj(x)))
+        if self.gate_proj.bias is not None:
+            return self.down_proj(ops.glu(self.gate_proj(x), self.up_proj(x)))
+        g, u = ops.multi_linear(x, (self.gate_proj.weight, self.up_proj.weight))
+        return ops.linear(ops.glu(g, u), self.down_proj.weight)
 
 
 class AttentionModule(nn.Module):
@@ -121,6 +124,19 @@ class TransformerBlock(nn.Module):
         x = x + self.self_attn(self.input_layernorm(x), mask=mask, position_ids=position_ids)
         return x + self.mlp(self.post_attention_layernorm(x))
 
+    def forward_fused(self, h: torch.Tensor, pending, mask=None, position_ids=None):
+        """Same block with every residual add fused into the norm that consumes it.  `pending` is the
+        previous block's MLP output not yet added to the stream h (None for the first block); returns
+        (h after the attention residual, this block's MLP output still to be added)."""
+        n1, n2 = self.input_layernorm, self.post_attention_layernorm
+        if pending is None:
+            y = n1(h)
+        else:
+            h, y = ops.add_rmsnorm(h, pending, n1.weight, n1.eps)
+        a = self.self_attn(y, mask=mask, position_ids=position_ids)
+        h, y = ops.add_rmsnorm(h, a, n2.weight, n2.eps)
+        return h, self.mlp(y)
+
 
 class Model(nn.Module):
     def __init__(self, args: ModelArgs):
@@ -138,9 +154,12 @@ class Model(nn.Module):
         B, S = inputs.shape
         mask = CausalMask(S) if attention_mask is None else attention_mask
         h = self.embed_tokens(inputs)
+        pending = None
         for layer in self.layers:
-            h = layer(h, mask=mask, position_ids=position_ids)
-        return self.norm(h)
+            h, pending = layer.forward_fused(h, pending, mask=mask, position_ids=position_ids)
+        if pending is None:
+            return self.norm(h)
+        return ops.add_rmsnorm(h, pending, self.norm.weight, self.norm.eps)[1]
 
     def padded_logits(self, inputs: torch.Tensor):
         """(logits [B*S, ld], V) with ld >= V, ld % 8 == 0 when the fused cross-entropy can take them

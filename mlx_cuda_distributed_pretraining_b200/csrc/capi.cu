@@ -44,6 +44,11 @@ size_t rmsnorm_bwd_workspace_bytes(int rows, int H);
 int rmsnorm_bwd(const void* dy, const void* x, const void* w, const float* rstd, void* dx,
                 float* dw, int rows, int H, int is_bf16, void* ws, size_t ws_bytes,
                 cudaStream_t stream);
+int add_rmsnorm_fwd(const void* x, const void* delta, const void* w, void* sum_out, void* y, float* rstd,
+                    int rows, int H, float eps, int is_bf16, cudaStream_t stream);
+int add_rmsnorm_bwd(const void* dy, const void* dres, const void* x, const void* w, const float* rstd,
+                    void* dx, float* dw, int rows, int H, int is_bf16, void* ws, size_t ws_bytes,
+                    cudaStream_t stream);
 int rope(const void* x, void* y, const float* cos_t, const float* sin_t, int B, int S, int NH,
          int D, int backward, int is_bf16, cudaStream_t stream);
 int glu_fwd(const void* g, const void* u, void* y, long long n, cudaStream_t stream);
@@ -159,6 +164,16 @@ int b200_rmsnorm_bwd(const void* dy, const void* x, const void* w, const float* 
                      size_t workspace_bytes, void* stream) {
   return b200::rmsnorm_bwd(dy, x, w, rstd, dx, dw_f32, rows, H, is_bf16, workspace, workspace_bytes,
                            S_(stream));
+}
+int b200_add_rmsnorm_fwd(const void* x, const void* delta, const void* w, void* sum_out, void* y,
+                         float* rstd, int rows, int H, float eps, int is_bf16, void* stream) {
+  return b200::add_rmsnorm_fwd(x, delta, w, sum_out, y, rstd, rows, H, eps, is_bf16, S_(stream));
+}
+int b200_add_rmsnorm_bwd(const void* dy, const void* dres, const void* x, const void* w,
+                         const float* rstd, void* dx, float* dw_f32, int rows, int H, int is_bf16,
+                         void* workspace, size_t workspace_bytes, void* stream) {
+  return b200::add_rmsnorm_bwd(dy, dres, x, w, rstd, dx, dw_f32, rows, H, is_bf16, workspace,
+                               workspace_bytes, S_(stream));
 }
 int b200_rope(const void* x, void* y, const float* cos_t, const float* sin_t, int B, int S, int NH,
               int D, int backward, int is_bf16, void* stream) {

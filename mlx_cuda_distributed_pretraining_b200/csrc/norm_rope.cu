@@ -45,10 +45,20 @@ __device__ __forceinline__ float block_sum_128(float v, float* red) {
   return t;
 }
 
+__device__ __forceinline__ float round_like(float v, const __nv_bfloat16*) {
+  return __bfloat162float(__float2bfloat16(v));
+}
+__device__ __forceinline__ float round_like(float v, const float*) { return v; }
+
+// ---- block-per-row kernels (any H <= 8192) -----------------------------------------------------------
+// Optional fused residual add (arch/llama.py:316-319, h = x + sublayer(norm(x))): with `delta` the row
+// normalised is s = round(x + delta) and s is also written to `sum_out`, exactly what the separate add
+// produced before.
 template <typename T, int NV>
 __global__ void __launch_bounds__(RN_THREADS)
-rmsnorm_fwd_kernel(const T* __restrict__ x, const T* __restrict__ w, T* __restrict__ y,
-                   float* __restrict__ rstd_out, int rows, int H, float eps) {
+rmsnorm_fwd_kernel(const T* __restrict__ x, const T* __restrict__ delta, const T* __restrict__ w,
+                   T* __restrict__ sum_out, T* __restrict__ y, float* __restrict__ rstd_out, int rows, int H,
+                   float eps) {
   __shared__ float red[4];
   float wv[NV][8];
 #pragma unroll
@@ -65,6 +75,13 @@ rmsnorm_fwd_kernel(const T* __restrict__ x, const T* __restrict__ w, T* __restri
       const int col = (v * RN_THREADS + threadIdx.x) * 8;
       if (col < H) {
         ld8(xr + col, xv[v]);
+        if (delta) {
+          float dv[8];
+          ld8(delta + (long long)row * H + col, dv);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) xv[v][j] = round_like(xv[v][j] + dv[j], x);
+          st8(sum_out + (long long)row * H + col, xv[v]);
+        }
 #pragma unroll
         for (int j = 0; j < 8; ++j) ss += xv[v][j] * xv[v][j];
       }
@@ -87,13 +104,14 @@ rmsnorm_fwd_kernel(const T* __restrict__ x, const T* __restrict__ w, T* __restri
   }
 }
 
-// dx = rstd * (dy*w - x * rstd^2 * mean(dy*w*x)) ; dw partials = sum over this CTA's rows of
+// dx = [dres +] rstd * (dy*w - x * rstd^2 * mean(dy*w*x)) ; dw partials = sum over this CTA's rows of
 // dy * x * rstd, written to dw_part[blockIdx.x, :] and summed by rmsnorm_dw_reduce_kernel (no atomics:
-// hundreds of CTAs hammering the same H addresses cost 4x the streaming time)
+// hundreds of CTAs hammering the same H addresses cost 4x the streaming time).  `dres` is the gradient
+// that reached the residual stream directly; adding it here removes autograd's separate accumulation pass.
 template <typename T, int NV>
 __global__ void __launch_bounds__(RN_THREADS)
-rmsnorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ w,
-                   const float* __restrict__ rstd_in, T* __restrict__ dx,
+rmsnorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ dres, const T* __restrict__ x,
+                   const T* __restrict__ w, const float* __restrict__ rstd_in, T* __restrict__ dx,
                    float* __restrict__ dw_part, int rows, int H) {
   __shared__ float red[4];
   float wv[NV][8], dwv[NV][8];
@@ -134,6 +152,12 @@ rmsnorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* _
         float o[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) o[j] = rstd * (gv[v][j] - xv[v][j] * c);
+        if (dres) {
+          float r[8];
+          ld8(dres + (long long)row * H + col, r);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] += r[j];
+        }
         st8(dxr + col, o);
       }
     }
@@ -145,21 +169,207 @@ rmsnorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* _
   }
 }
 
-// dw[c] = sum_b dw_part[b, c]
-__global__ void __launch_bounds__(256)
-rmsnorm_dw_reduce_kernel(const float* __restrict__ dw_part, float* __restrict__ dw, int nblocks, int H) {
-  const int c = blockIdx.x * 256 + threadIdx.x;
-  if (c >= H) return;
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-  int b = 0;
-  for (; b + 3 < nblocks; b += 4) {
-    s0 += dw_part[(long long)b * H + c];
-    s1 += dw_part[(long long)(b + 1) * H + c];
-    s2 += dw_part[(long long)(b + 2) * H + c];
-    s3 += dw_part[(long long)(b + 3) * H + c];
+// ---- warp-per-row kernels (H <= 1024): no block barrier per row, four independent rows in flight per
+// ---- CTA, so the loads of one row overlap the reduction and stores of its neighbours ------------------
+constexpr int RW_WARPS = RN_THREADS / 32;
+
+template <typename T, int NVW>
+__global__ void __launch_bounds__(RN_THREADS)
+rmsnorm_fwd_warp_kernel(const T* __restrict__ x, const T* __restrict__ delta, const T* __restrict__ w,
+                        T* __restrict__ sum_out, T* __restrict__ y, float* __restrict__ rstd_out, int rows,
+                        int H, float eps) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float wv[NVW][8];
+#pragma unroll
+  for (int v = 0; v < NVW; ++v) {
+    const int col = (v * 32 + lane) * 8;
+    if (col < H) ld8(w + col, wv[v]);
   }
-  for (; b < nblocks; ++b) s0 += dw_part[(long long)b * H + c];
-  dw[c] = (s0 + s1) + (s2 + s3);
+  for (int row = blockIdx.x * RW_WARPS + warp; row < rows; row += gridDim.x * RW_WARPS) {
+    const long long base = (long long)row * H;
+    float xv[NVW][8];
+#pragma unroll
+    for (int v = 0; v < NVW; ++v) {
+      const int col = (v * 32 + lane) * 8;
+      if (col < H) ld8(x + base + col, xv[v]);
+    }
+    if (delta) {
+#pragma unroll
+      for (int v = 0; v < NVW; ++v) {
+        const int col = (v * 32 + lane) * 8;
+        if (col < H) {
+          float dv[8];
+          ld8(delta + base + col, dv);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) xv[v][j] = round_like(xv[v][j] + dv[j], x);
+          st8(sum_out + base + col, xv[v]);
+        }
+      }
+    }
+    float ss = 0.f;
+#pragma unroll
+    for (int v = 0; v < NVW; ++v) {
+      const int col = (v * 32 + lane) * 8;
+      if (col < H) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ss += xv[v][j] * xv[v][j];
+      }
+    }
+    const float tot = warp_sum(ss);
+    const float rstd = 1.0f / sqrtf(tot / (float)H + eps);
+    if (lane == 0 && rstd_out) rstd_out[row] = rstd;
+#pragma unroll
+    for (int v = 0; v < NVW; ++v) {
+      const int col = (v * 32 + lane) * 8;
+      if (col < H) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = xv[v][j] * rstd * wv[v][j];
+        st8(y + base + col, o);
+      }
+    }
+  }
+}
+
+// Packed row segments: the backward pass keeps x and dy of the whole row in registers between the two
+// passes (dot product, then dx); holding bf16 rows packed halves that footprint and buys a fourth CTA per SM.
+template <typename T> struct Raw8;
+template <> struct Raw8<__nv_bfloat16> { uint4 r; };
+template <> struct Raw8<float> { float4 a, b; };
+__device__ __forceinline__ void ldraw(const __nv_bfloat16* p, Raw8<__nv_bfloat16>& o) {
+  o.r = *reinterpret_cast<const uint4*>(p);
+}
+__device__ __forceinline__ void ldraw(const float* p, Raw8<float>& o) {
+  o.a = *reinterpret_cast<const float4*>(p);
+  o.b = *reinterpret_cast<const float4*>(p + 4);
+}
+__device__ __forceinline__ void unraw(const Raw8<__nv_bfloat16>& i, float* f) {
+  const float2 v0 = unpack_bf16x2(i.r.x), v1 = unpack_bf16x2(i.r.y), v2 = unpack_bf16x2(i.r.z),
+               v3 = unpack_bf16x2(i.r.w);
+  f[0] = v0.x; f[1] = v0.y; f[2] = v1.x; f[3] = v1.y;
+  f[4] = v2.x; f[5] = v2.y; f[6] = v3.x; f[7] = v3.y;
+}
+__device__ __forceinline__ void unraw(const Raw8<float>& i, float* f) {
+  f[0] = i.a.x; f[1] = i.a.y; f[2] = i.a.z; f[3] = i.a.w;
+  f[4] = i.b.x; f[5] = i.b.y; f[6] = i.b.z; f[7] = i.b.w;
+}
+
+template <typename T, int NVW>
+__global__ void __launch_bounds__(RN_THREADS, 4)
+rmsnorm_bwd_warp_kernel(const T* __restrict__ dy, const T* __restrict__ dres, const T* __restrict__ x,
+                        const T* __restrict__ w, const float* __restrict__ rstd_in, T* __restrict__ dx,
+                        float* __restrict__ dw_part, int rows, int H) {
+  extern __shared__ float dw_s[];  // [RW_WARPS - 1][H]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float dwv[NVW][8];
+#pragma unroll
+  for (int v = 0; v < NVW; ++v) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dwv[v][j] = 0.f;
+  }
+  for (int row = blockIdx.x * RW_WARPS + warp; row < rows; row += gridDim.x * RW_WARPS) {
+    const long long base = (long long)row * H;
+    const float rstd = rstd_in[row];
+    Raw8<T> xr[NVW], gr[NVW];
+#pragma unroll
+    for (int v = 0; v < NVW; ++v) {
+      const int col = (v * 32 + lane) * 8;
+      if (col < H) {
+        ldraw(x + base + col, xr[v]);
+        ldraw(dy + base + col, gr[v]);
+      }
+    }
+    float dot = 0.f;
+#pragma unroll
+    for (int v = 0; v < NVW; ++v) {
+      const int col = (v * 32 + lane) * 8;
+      if (col < H) {
+        float xv[8], gv[8], wv[8];
+        unraw(xr[v], xv);
+        unraw(gr[v], gv);
+        ld8(w + col, wv);  // 2 KB, L1-resident
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float gx = gv[j] * xv[j];
+          dwv[v][j] += gx * rstd;
+          dot += gx * wv[j];
+        }
+      }
+    }
+    const float c = warp_sum(dot) / (float)H * rstd * rstd;
+#pragma unroll
+    for (int v = 0; v < NVW; ++v) {
+      const int col = (v * 32 + lane) * 8;
+      if (col < H) {
+        float xv[8], gv[8], wv[8], o[8];
+        unraw(xr[v], xv);
+        unraw(gr[v], gv);
+        ld8(w + col, wv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = rstd * (gv[j] * wv[j] - xv[j] * c);
+        if (dres) {
+          float r[8];
+          ld8(dres + base + col, r);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] += r[j];
+        }
+        st8(dx + base + col, o);
+      }
+    }
+  }
+  // fold the four warps' dw partials through smem, one partial row per CTA
+  if (warp > 0) {
+#pragma unroll
+    for (int v = 0; v < NVW; ++v) {
+      const int col = (v * 32 + lane) * 8;
+      if (col < H) st8(dw_s + (warp - 1) * H + col, dwv[v]);
+    }
+  }
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int v = 0; v < NVW; ++v) {
+      const int col = (v * 32 + lane) * 8;
+      if (col < H) {
+#pragma unroll
+        for (int u = 0; u < RW_WARPS - 1; ++u) {
+          float t[8];
+          ld8(dw_s + u * H + col, t);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) dwv[v][j] += t[j];
+        }
+        st8(dw_part + (long long)blockIdx.x * H + col, dwv[v]);
+      }
+    }
+  }
+}
+
+// dw[c] = sum_b dw_part[b, c].  One CTA per 32 columns: warp r sums partial rows r, r+32, ... (128-byte
+// coalesced row segments, independent loads in flight), then the 32 row groups fold through smem.
+__global__ void __launch_bounds__(1024)
+rmsnorm_dw_reduce_kernel(const float* __restrict__ dw_part, float* __restrict__ dw, int nblocks, int H) {
+  __shared__ float part[32][33];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  if (c < H) {
+    int b = ry;
+    for (; b + 96 < nblocks; b += 128) {
+      s0 += dw_part[(long long)b * H + c];
+      s1 += dw_part[(long long)(b + 32) * H + c];
+      s2 += dw_part[(long long)(b + 64) * H + c];
+      s3 += dw_part[(long long)(b + 96) * H + c];
+    }
+    for (; b < nblocks; b += 32) s0 += dw_part[(long long)b * H + c];
+  }
+  part[ry][cx] = (s0 + s1) + (s2 + s3);
+  __syncthreads();
+  if (ry == 0 && c < H) {
+    float t = 0.f;
+#pragma unroll
+    for (int r = 0; r < 32; ++r) t += part[r][cx];
+    dw[c] = t;
+  }
 }
 
 // x: [B, S, NH, D]; cos/sin: [S, D/2] fp32. out[2i] = x[2i]*c - x[2i+1]*s ; out[2i+1] = x[2i]*s +
@@ -187,36 +397,60 @@ rope_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __restrict_
   }
 }
 
+constexpr int RW_MAX_H = 1024;  // NVW <= 4: beyond that the packed row no longer fits 128 registers
+
 template <typename T>
-int rmsnorm_fwd_t(const T* x, const T* w, T* y, float* rstd, int rows, int H, float eps,
-                  cudaStream_t stream) {
+int rmsnorm_fwd_t(const T* x, const T* delta, const T* w, T* sum_out, T* y, float* rstd, int rows, int H,
+                  float eps, cudaStream_t stream) {
+  if (H <= RW_MAX_H) {
+    const int want = (rows + RW_WARPS - 1) / RW_WARPS;
+    const int grid = want < num_sms() * 8 ? want : num_sms() * 8;
+    const int nvw = (H + 255) / 256;
+    if (nvw <= 1) rmsnorm_fwd_warp_kernel<T, 1><<<grid, RN_THREADS, 0, stream>>>(x, delta, w, sum_out, y, rstd, rows, H, eps);
+    else if (nvw <= 2) rmsnorm_fwd_warp_kernel<T, 2><<<grid, RN_THREADS, 0, stream>>>(x, delta, w, sum_out, y, rstd, rows, H, eps);
+    else if (nvw <= 4) rmsnorm_fwd_warp_kernel<T, 4><<<grid, RN_THREADS, 0, stream>>>(x, delta, w, sum_out, y, rstd, rows, H, eps);
+    else rmsnorm_fwd_warp_kernel<T, 8><<<grid, RN_THREADS, 0, stream>>>(x, delta, w, sum_out, y, rstd, rows, H, eps);
+    B200_CHECK_LAUNCH();
+    return B200_OK;
+  }
   const int nv = (H / 8 + RN_THREADS - 1) / RN_THREADS;
   const int grid = rows < num_sms() * 16 ? rows : num_sms() * 16;
   switch (nv) {
-    case 1: rmsnorm_fwd_kernel<T, 1><<<grid, RN_THREADS, 0, stream>>>(x, w, y, rstd, rows, H, eps); break;
-    case 2: rmsnorm_fwd_kernel<T, 2><<<grid, RN_THREADS, 0, stream>>>(x, w, y, rstd, rows, H, eps); break;
-    case 3: case 4: rmsnorm_fwd_kernel<T, 4><<<grid, RN_THREADS, 0, stream>>>(x, w, y, rstd, rows, H, eps); break;
-    default: rmsnorm_fwd_kernel<T, RN_MAX_VEC><<<grid, RN_THREADS, 0, stream>>>(x, w, y, rstd, rows, H, eps); break;
+    case 1: case 2: case 3: case 4:
+      rmsnorm_fwd_kernel<T, 4><<<grid, RN_THREADS, 0, stream>>>(x, delta, w, sum_out, y, rstd, rows, H, eps); break;
+    default:
+      rmsnorm_fwd_kernel<T, RN_MAX_VEC><<<grid, RN_THREADS, 0, stream>>>(x, delta, w, sum_out, y, rstd, rows, H, eps); break;
   }
   B200_CHECK_LAUNCH();
   return B200_OK;
 }
 
-inline int rmsnorm_bwd_grid(int rows) { return rows < num_sms() * 4 ? rows : num_sms() * 4; }
+inline int rmsnorm_bwd_grid(int rows, int H) {
+  if (H <= RW_MAX_H) {
+    const int want = (rows + RW_WARPS - 1) / RW_WARPS;
+    return want < num_sms() * 4 ? want : num_sms() * 4;
+  }
+  return rows < num_sms() * 4 ? rows : num_sms() * 4;
+}
 
 template <typename T>
-int rmsnorm_bwd_t(const T* dy, const T* x, const T* w, const float* rstd, T* dx, float* dw,
+int rmsnorm_bwd_t(const T* dy, const T* dres, const T* x, const T* w, const float* rstd, T* dx, float* dw,
                   float* dw_part, int rows, int H, cudaStream_t stream) {
-  const int nv = (H / 8 + RN_THREADS - 1) / RN_THREADS;
-  const int grid = rmsnorm_bwd_grid(rows);
-  switch (nv) {
-    case 1: rmsnorm_bwd_kernel<T, 1><<<grid, RN_THREADS, 0, stream>>>(dy, x, w, rstd, dx, dw_part, rows, H); break;
-    case 2: rmsnorm_bwd_kernel<T, 2><<<grid, RN_THREADS, 0, stream>>>(dy, x, w, rstd, dx, dw_part, rows, H); break;
-    case 3: case 4: rmsnorm_bwd_kernel<T, 4><<<grid, RN_THREADS, 0, stream>>>(dy, x, w, rstd, dx, dw_part, rows, H); break;
-    default: rmsnorm_bwd_kernel<T, RN_MAX_VEC><<<grid, RN_THREADS, 0, stream>>>(dy, x, w, rstd, dx, dw_part, rows, H); break;
+  const int grid = rmsnorm_bwd_grid(rows, H);
+  if (H <= RW_MAX_H) {
+    const int nvw = (H + 255) / 256;
+    const size_t smem = (size_t)(RW_WARPS - 1) * H * sizeof(float);
+    if (nvw <= 1) rmsnorm_bwd_warp_kernel<T, 1><<<grid, RN_THREADS, smem, stream>>>(dy, dres, x, w, rstd, dx, dw_part, rows, H);
+    else if (nvw <= 2) rmsnorm_bwd_warp_kernel<T, 2><<<grid, RN_THREADS, smem, stream>>>(dy, dres, x, w, rstd, dx, dw_part, rows, H);
+    else if (nvw <= 4) rmsnorm_bwd_warp_kernel<T, 4><<<grid, RN_THREADS, smem, stream>>>(dy, dres, x, w, rstd, dx, dw_part, rows, H);
+    else rmsnorm_bwd_warp_kernel<T, 8><<<grid, RN_THREADS, smem, stream>>>(dy, dres, x, w, rstd, dx, dw_part, rows, H);
+  } else {
+    const int nv = (H / 8 + RN_THREADS - 1) / RN_THREADS;
+    if (nv <= 4) rmsnorm_bwd_kernel<T, 4><<<grid, RN_THREADS, 0, stream>>>(dy, dres, x, w, rstd, dx, dw_part, rows, H);
+    else rmsnorm_bwd_kernel<T, RN_MAX_VEC><<<grid, RN_THREADS, 0, stream>>>(dy, dres, x, w, rstd, dx, dw_part, rows, H);
   }
   B200_CHECK_LAUNCH();
-  rmsnorm_dw_reduce_kernel<<<(H + 255) / 256, 256, 0, stream>>>(dw_part, dw, grid, H);
+  rmsnorm_dw_reduce_kernel<<<(H + 31) / 32, 1024, 0, stream>>>(dw_part, dw, grid, H);
   B200_CHECK_LAUNCH();
   return B200_OK;
 }
@@ -225,40 +459,55 @@ inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) 
 
 }  // namespace
 
-int rmsnorm_fwd(const void* x, const void* w, void* y, float* rstd, int rows, int H, float eps,
-                int is_bf16, cudaStream_t stream) {
+int add_rmsnorm_fwd(const void* x, const void* delta, const void* w, void* sum_out, void* y, float* rstd,
+                    int rows, int H, float eps, int is_bf16, cudaStream_t stream) {
   B200_CHECK_ARG(rows > 0 && H > 0 && H % 8 == 0 && H <= RN_THREADS * 8 * RN_MAX_VEC,
                  "rmsnorm_fwd: unsupported shape rows=%d H=%d (H %% 8 == 0, H <= %d)", rows, H,
                  RN_THREADS * 8 * RN_MAX_VEC);
-  B200_CHECK_ARG(al16(x) && al16(w) && al16(y), "rmsnorm_fwd: 16-byte alignment required");
+  B200_CHECK_ARG(al16(x) && al16(w) && al16(y) && al16(delta) && al16(sum_out),
+                 "rmsnorm_fwd: 16-byte alignment required");
+  B200_CHECK_ARG((delta == nullptr) == (sum_out == nullptr),
+                 "add_rmsnorm_fwd: delta and sum_out must be given together");
   if (is_bf16)
-    return rmsnorm_fwd_t<__nv_bfloat16>((const __nv_bfloat16*)x, (const __nv_bfloat16*)w,
-                                        (__nv_bfloat16*)y, rstd, rows, H, eps, stream);
-  return rmsnorm_fwd_t<float>((const float*)x, (const float*)w, (float*)y, rstd, rows, H, eps,
-                              stream);
+    return rmsnorm_fwd_t<__nv_bfloat16>((const __nv_bfloat16*)x, (const __nv_bfloat16*)delta,
+                                        (const __nv_bfloat16*)w, (__nv_bfloat16*)sum_out, (__nv_bfloat16*)y,
+                                        rstd, rows, H, eps, stream);
+  return rmsnorm_fwd_t<float>((const float*)x, (const float*)delta, (const float*)w, (float*)sum_out,
+                              (float*)y, rstd, rows, H, eps, stream);
+}
+
+int rmsnorm_fwd(const void* x, const void* w, void* y, float* rstd, int rows, int H, float eps,
+                int is_bf16, cudaStream_t stream) {
+  return add_rmsnorm_fwd(x, nullptr, w, nullptr, y, rstd, rows, H, eps, is_bf16, stream);
 }
 
 size_t rmsnorm_bwd_workspace_bytes(int rows, int H) {
-  return (size_t)rmsnorm_bwd_grid(rows) * H * sizeof(float);
+  return (size_t)rmsnorm_bwd_grid(rows, H) * H * sizeof(float);
 }
 
-int rmsnorm_bwd(const void* dy, const void* x, const void* w, const float* rstd, void* dx,
-                float* dw, int rows, int H, int is_bf16, void* ws, size_t ws_bytes,
-                cudaStream_t stream) {
+int add_rmsnorm_bwd(const void* dy, const void* dres, const void* x, const void* w, const float* rstd,
+                    void* dx, float* dw, int rows, int H, int is_bf16, void* ws, size_t ws_bytes,
+                    cudaStream_t stream) {
   B200_CHECK_ARG(rows > 0 && H > 0 && H % 8 == 0 && H <= RN_THREADS * 8 * RN_MAX_VEC,
                  "rmsnorm_bwd: unsupported shape rows=%d H=%d", rows, H);
-  B200_CHECK_ARG(al16(dy) && al16(x) && al16(w) && al16(dx), "rmsnorm_bwd: alignment");
+  B200_CHECK_ARG(al16(dy) && al16(x) && al16(w) && al16(dx) && al16(dres), "rmsnorm_bwd: alignment");
   if (ws == nullptr || ws_bytes < rmsnorm_bwd_workspace_bytes(rows, H)) {
     set_error("rmsnorm_bwd: workspace too small (%zu < %zu)", ws_bytes, rmsnorm_bwd_workspace_bytes(rows, H));
     return B200_ERR_WORKSPACE;
   }
   float* part = reinterpret_cast<float*>(ws);
   if (is_bf16)
-    return rmsnorm_bwd_t<__nv_bfloat16>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x,
-                                        (const __nv_bfloat16*)w, rstd, (__nv_bfloat16*)dx, dw, part,
-                                        rows, H, stream);
-  return rmsnorm_bwd_t<float>((const float*)dy, (const float*)x, (const float*)w, rstd, (float*)dx,
-                              dw, part, rows, H, stream);
+    return rmsnorm_bwd_t<__nv_bfloat16>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)dres,
+                                        (const __nv_bfloat16*)x, (const __nv_bfloat16*)w, rstd,
+                                        (__nv_bfloat16*)dx, dw, part, rows, H, stream);
+  return rmsnorm_bwd_t<float>((const float*)dy, (const float*)dres, (const float*)x, (const float*)w, rstd,
+                              (float*)dx, dw, part, rows, H, stream);
+}
+
+int rmsnorm_bwd(const void* dy, const void* x, const void* w, const float* rstd, void* dx,
+                float* dw, int rows, int H, int is_bf16, void* ws, size_t ws_bytes,
+                cudaStream_t stream) {
+  return add_rmsnorm_bwd(dy, nullptr, x, w, rstd, dx, dw, rows, H, is_bf16, ws, ws_bytes, stream);
 }
 
 int rope(const void* x, void* y, const float* cos_t, const float* sin_t, int B, int S, int NH,

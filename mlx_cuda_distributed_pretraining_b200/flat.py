@@ -117,6 +117,7 @@ class ParamStore:
                     self.shadow[o:o + n].view(shape).copy_(self.master[o:o + n].view(shape))
                 p.data = compute[o:o + n].view(shape)
                 p.grad = self.grad[o:o + n].view(shape)
+                p._b200_flat_grad = True   # ops._accumulate_wgrad may GEMM straight into this view
         self.params = params
         model._b200_store = self
 

@@ -277,6 +277,116 @@ def rmsnorm(x: torch.Tensor, w: torch.Tensor, eps: float = 1e-5) -> torch.Tensor
     return _RMSNormFn.apply(x, w, eps)
 
 
+class _AddRMSNormFn(torch.autograd.Function):
+    """(x, delta) -> (s = x + delta, rmsnorm(s) * w): the residual add of arch/llama.py:316-319 fused with
+    the norm that reads its result; backward folds the residual-stream gradient into the norm's dx."""
+
+    @staticmethod
+    def forward(ctx, x, delta, w, eps):
+        xs, ds = x.contiguous(), delta.contiguous()
+        rows, H = xs.numel() // xs.shape[-1], xs.shape[-1]
+        s = torch.empty_like(xs)
+        y = torch.empty_like(xs)
+        rstd = torch.empty(rows, device=x.device, dtype=torch.float32)
+        wc = w.contiguous().to(xs.dtype)
+        check(lib().b200_add_rmsnorm_fwd(xs.data_ptr(), ds.data_ptr(), wc.data_ptr(), s.data_ptr(), y.data_ptr(),
+                                         rstd.data_ptr(), rows, H, float(eps), _is_bf16(xs, "x"), _stream()),
+              "b200_add_rmsnorm_fwd")
+        ctx.save_for_backward(s, wc, rstd)
+        ctx.w_dtype = w.dtype
+        ctx.set_materialize_grads(False)
+        return s, y
+
+    @staticmethod
+    def backward(ctx, ds, dy):
+        s, wc, rstd = ctx.saved_tensors
+        if dy is None:
+            return ds, ds, None, None
+        dy = dy.contiguous()
+        rows, H = s.numel() // s.shape[-1], s.shape[-1]
+        dx = torch.empty_like(s)
+        dw = torch.empty(H, device=s.device, dtype=torch.float32)
+        ws = torch.empty(int(lib().b200_rmsnorm_bwd_workspace_bytes(rows, H)), device=s.device, dtype=torch.uint8)
+        dres = ds.contiguous() if ds is not None else None
+        check(lib().b200_add_rmsnorm_bwd(dy.data_ptr(), dres.data_ptr() if dres is not None else None,
+                                         s.data_ptr(), wc.data_ptr(), rstd.data_ptr(), dx.data_ptr(),
+                                         dw.data_ptr(), rows, H, _is_bf16(s, "x"), ws.data_ptr(), ws.numel(),
+                                         _stream()), "b200_add_rmsnorm_bwd")
+        return dx, dx, dw.to(ctx.w_dtype), None
+
+
+def add_rmsnorm(x: torch.Tensor, delta: torch.Tensor, w: torch.Tensor, eps: float = 1e-5):
+    """Returns (x + delta, rmsnorm(x + delta) * w)."""
+    return _AddRMSNormFn.apply(x, delta, w, eps)
+
+
+def _accumulate_wgrad(w: torch.Tensor, dy2: torch.Tensor, x2: torch.Tensor):
+    """dW = dy^T x.  When the weight's .grad is a view of the flat gradient buffer (flat.ParamStore), the
+    GEMM accumulates straight into it (beta = 1 epilogue) and autograd gets None: no temporary, no
+    separate AccumulateGrad add kernel per parameter."""
+    g = w.grad
+    if getattr(w, "_b200_flat_grad", False) and g is not None and g.dtype == dy2.dtype:
+        g.addmm_(dy2.t(), x2)
+        return None
+    return dy2.t() @ x2
+
+
+class _LinearFn(torch.autograd.Function):
+    """y = x W^T (bias-free nn.Linear, arch/llama.py projections) through the library GEMM."""
+
+    @staticmethod
+    def forward(ctx, x, w):
+        ctx.save_for_backward(x, w)
+        return torch.nn.functional.linear(x, w)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        dx = torch.matmul(dy, w) if ctx.needs_input_grad[0] else None
+        dw = None
+        if ctx.needs_input_grad[1]:
+            dw = _accumulate_wgrad(w, dy.reshape(-1, dy.shape[-1]), x.reshape(-1, x.shape[-1]))
+        return dx, dw
+
+
+class _MultiLinearFn(torch.autograd.Function):
+    """Several bias-free projections of the same input (q/k/v, gate/up).  Backward accumulates
+    dx = sum_i dy_i W_i inside the GEMM epilogues instead of autograd's extra add passes."""
+
+    @staticmethod
+    def forward(ctx, x, *ws):
+        ctx.save_for_backward(x, *ws)
+        ctx.set_materialize_grads(False)
+        return tuple(torch.nn.functional.linear(x, w) for w in ws)
+
+    @staticmethod
+    def backward(ctx, *dys):
+        x, *ws = ctx.saved_tensors
+        x2 = x.reshape(-1, x.shape[-1])
+        dx2 = None
+        dws = []
+        for i, (dy, w) in enumerate(zip(dys, ws)):
+            if dy is None:
+                dws.append(None)
+                continue
+            dy2 = dy.reshape(-1, dy.shape[-1])
+            if ctx.needs_input_grad[0]:
+                if dx2 is None:
+                    dx2 = dy2 @ w
+                else:
+                    dx2.addmm_(dy2, w)
+            dws.append(_accumulate_wgrad(w, dy2, x2) if ctx.needs_input_grad[1 + i] else None)
+        return (dx2.view(x.shape) if dx2 is not None else None, *dws)
+
+
+def linear(x: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+    return _LinearFn.apply(x, w)
+
+
+def multi_linear(x: torch.Tensor, ws) -> tuple:
+    return _MultiLinearFn.apply(x, *ws)
+
+
 def rope_tables(seq_len: int, head_dim: int, theta: float, device) -> Tuple[torch.Tensor, torch.Tensor]:
     """cos/sin [S, D/2] fp32: angle = pos * theta^(-2i/D) (arch/llama_standard.py:74-75,83-84)."""
     freqs = torch.pow(torch.tensor(float(theta), dtype=torch.float32),

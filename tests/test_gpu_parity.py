@@ -185,6 +185,63 @@ def test_rmsnorm_fwd_bwd(ops, dt, tol, H):
     assert rel(y, yr) < tol and rel(x.grad, xr.grad) < tol and rel(w.grad, wr.grad) < max(tol, 5e-6)
 
 
+@pytest.mark.parametrize("dt,tol", [(torch.bfloat16, 6e-3), (torch.float32, 2e-6)])
+@pytest.mark.parametrize("H", [72, 1024, 1536, 4096])
+def test_add_rmsnorm_fwd_bwd(ops, dt, tol, H):
+    """Residual add fused into the norm (arch/llama.py:316-319) == separate add + RMSNorm, forward and
+    backward, including the gradient that reaches the sum directly."""
+    torch.manual_seed(15)
+    x = torch.randn(2, 41, H, device="cuda").to(dt).requires_grad_(True)
+    d = torch.randn(2, 41, H, device="cuda").to(dt).requires_grad_(True)
+    w = (torch.rand(H, device="cuda") + 0.5).to(dt).requires_grad_(True)
+    s, y = ops.add_rmsnorm(x, d, w, 1e-5)
+    assert torch.equal(s, (x + d).detach())                      # same rounding as the separate add
+    ds, dy = torch.randn_like(s), torch.randn_like(y)
+    torch.autograd.backward([s, y], [ds, dy])
+    xr, dr, wr = (t.detach().float().cpu().requires_grad_(True) for t in (x, d, w))
+    sr = (xr + dr).to(dt).float() if dt == torch.bfloat16 else xr + dr
+    sr = xr + dr + (sr - (xr + dr)).detach()                     # straight-through rounding
+    yr = R.rmsnorm(sr, wr, 1e-5)
+    torch.autograd.backward([sr, yr], [ds.float().cpu(), dy.float().cpu()])
+    assert rel(y, yr) < tol
+    assert rel(x.grad, xr.grad) < tol and torch.equal(x.grad, d.grad)
+    assert rel(w.grad, wr.grad) < max(tol, 5e-6)
+    # y alone used (final norm of the model): no residual gradient
+    x2, d2 = x.detach().clone().requires_grad_(True), d.detach().clone().requires_grad_(True)
+    _, y2 = ops.add_rmsnorm(x2, d2, w, 1e-5)
+    y2.backward(dy)
+    xr2 = (x.detach() + d.detach()).float().cpu().requires_grad_(True)
+    R.rmsnorm(xr2, w.detach().float().cpu(), 1e-5).backward(dy.float().cpu())
+    assert rel(x2.grad, xr2.grad) < tol
+
+
+def test_linear_direct_wgrad(ops):
+    """ops.linear / ops.multi_linear == nn.functional.linear; with a flat-buffer .grad the weight gradient
+    is accumulated in place by the GEMM and autograd sees None."""
+    torch.manual_seed(16)
+    x = (torch.randn(4, 33, 256, device="cuda") * 0.5).to(torch.bfloat16).requires_grad_(True)
+    ws = [(torch.randn(n, 256, device="cuda") * 0.1).to(torch.bfloat16).requires_grad_(True) for n in (128, 64, 64)]
+    outs = ops.multi_linear(x, ws)
+    dys = [torch.randn_like(o) for o in outs]
+    torch.autograd.backward(list(outs), dys)
+    xr = x.detach().float().requires_grad_(True)
+    wrs = [w.detach().float().requires_grad_(True) for w in ws]
+    outs_r = [torch.nn.functional.linear(xr, w) for w in wrs]
+    torch.autograd.backward(outs_r, [d.float() for d in dys])
+    assert all(rel(o, r) < 4e-3 for o, r in zip(outs, outs_r))
+    assert rel(x.grad, xr.grad) < 6e-3
+    assert all(rel(w.grad, wr.grad) < 4e-3 for w, wr in zip(ws, wrs))
+    # flat-gradient mode: accumulate into the existing .grad, twice
+    flat = torch.zeros(128 * 256, device="cuda", dtype=torch.bfloat16)
+    w0 = ws[0].detach().clone().requires_grad_(True)
+    w0.grad = flat.view(128, 256)
+    w0._b200_flat_grad = True
+    for _ in range(2):
+        ops.linear(x.detach(), w0).backward(dys[0])
+    assert w0.grad.data_ptr() == flat.data_ptr()
+    assert rel(flat.view(128, 256), 2 * wrs[0].grad) < 6e-3
+
+
 def test_rmsnorm_golden(ops, golden):
     x, w = torch.from_numpy(golden["rms_x"]).cuda(), torch.from_numpy(golden["rms_w"]).cuda()
     assert rel(ops.rmsnorm(x, w, 1e-5), golden["rms_y"]) < 2e-6

@@ -30,4 +30,18 @@ ev = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUD
 tot = sum(e.device_time for e in ev) / 4 / 1e3 if hasattr(ev[0], "device_time") else sum(e.cuda_time for e in ev) / 4 / 1e3
 t0 = min(e.time_range.start for e in ev); t1 = max(e.time_range.end for e in ev)
 print(f"GPU kernel time per step: {tot:.2f} ms; GPU span per step: {(t1 - t0) / 4 / 1e3:.2f} ms; kernels/step: {len(ev) // 4}")
-print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=28, max_name_column_width=70))
+import collections, re
+agg = collections.defaultdict(lambda: [0, 0.0])
+for e in ev:
+    name = re.sub(r"void |b200::|\(anonymous namespace\)::|at::native::|<unnamed>::", "", e.name)
+    name = re.sub(r"\(.*", "", name)[:90]
+    agg[name][0] += 1
+    agg[name][1] += (e.device_time if hasattr(e, "device_time") else e.cuda_time)
+lines = []
+for name, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:45]:
+    lines.append(f"{t / 4 / 1e3:8.3f} ms  {n // 4:5d}x  {name}")
+out = "\n".join(lines)
+print(out)
+(ROOT / "gpurun_out").mkdir(exist_ok=True)
+(ROOT / "gpurun_out" / "step_breakdown.txt").write_text(
+    f"GPU kernel time per step: {tot:.2f} ms; span {(t1 - t0) / 4 / 1e3:.2f} ms; kernels/step {len(ev) // 4}\n" + out + "\n")

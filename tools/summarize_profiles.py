@@ -19,7 +19,7 @@ KEYS = ["gpu__time_duration.sum", "sm__pipe_tensor_cycles_active.avg.pct_of_peak
         "dram__bytes_read.sum", "dram__bytes_write.sum", "sm__warps_active.avg.pct_of_peak_sustained_active",
         "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "sm__cycles_elapsed.avg",
         "lts__t_bytes.sum", "lts__t_sector_hit_rate.pct"]
-MINE = ("gemm_bf16_tc", "attn_", "rmsnorm", "rope_kernel", "muon_", "axpy", "adamw", "clip_accum", "sumsq",
+MINE = ("gemm_bf16_tc", "gemm2_bf16_tc", "splitk_", "delta_kernel", "attn_", "rmsnorm", "rope_kernel", "muon_", "axpy", "adamw", "clip_accum", "sumsq",
         "ns_scales", "sgd_momentum", "f32_to_bf16", "ema_split", "graft_update", "split_bf16", "glu_", "ce_")
 
 
