@@ -471,6 +471,10 @@ class Trainer:
             self.store.ensure_acc()
         self.optimizer.use_accumulated = self.use_acc
         self.optimizer.grad_scale = 1.0 / self.world if self.distributed else 1.0
+        if hasattr(self.optimizer, "shard_ns"):
+            # owner-computes Newton-Schulz across the data-parallel ranks (SURVEY 8e fused mode)
+            self.optimizer.shard_ns = bool(self.distributed and self.world > 1 and
+                                           os.environ.get("B200_SHARD_NS", "1") != "0")
         self.validation_steps = self.config.logging.steps.get("validation_interval", 0)
         self._pin = None
 

@@ -85,6 +85,42 @@ def partition_by_cost(costs: List[float], world: int) -> List[int]:
     return owner
 
 
+def chunk_ranges(batch: int, world: int) -> Tuple[int, List[Tuple[int, int]]]:
+    """Owner-computes split of one shape group's `batch` matrices: equal chunks of c = ceil(batch/world)
+    consecutive matrices (the tail ranks may own fewer or none).  Returns (c, [(lo, hi) per rank]).
+    Groups smaller than the world are handled by `small_group_owner` + broadcast instead, so that a
+    single 32003 x 1024 embedding is not gathered world-size times."""
+    c = -(-batch // world)
+    return c, [(min(r * c, batch), min((r + 1) * c, batch)) for r in range(world)]
+
+
+def small_group_owner(index: int, world: int) -> int:
+    """Owner of matrix `index` of a group with fewer matrices than ranks: filled from the LAST rank
+    down, because chunk_ranges leaves the tail ranks with the least work."""
+    return world - 1 - (index % world)
+
+
+def all_gather_chunks_(full: torch.Tensor, chunk_elems: int, async_op: bool = False):
+    """In-place all-gather: rank r contributes full[r*chunk : (r+1)*chunk], every rank ends with all
+    world*chunk elements.  Returns the work handle when async_op (None on a single process)."""
+    if not (dist.is_initialized() and dist.get_world_size() > 1):
+        return None
+    r = dist.get_rank()
+    w = dist.get_world_size()
+    assert full.numel() >= w * chunk_elems, "gather buffer smaller than world * chunk"
+    out = full[:w * chunk_elems]
+    mine = out[r * chunk_elems:(r + 1) * chunk_elems]
+    if full.device.type == "cpu":   # gloo: no in-place gather; clone the contribution
+        mine = mine.clone()
+    return dist.all_gather_into_tensor(out, mine, async_op=async_op)
+
+
+def broadcast_async_(t: torch.Tensor, src: int):
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        return dist.broadcast(t, src=src, async_op=True)
+    return None
+
+
 def destroy() -> None:
     if dist.is_initialized():
         dist.destroy_process_group()

@@ -11,6 +11,14 @@ Per 2-D shape group the step is: fused momentum+Nesterov+sum-of-squares pass -> 
 Newton-Schulz on tcgen05 -> fused `p += -lr*max(1,r/c)^0.5 * X` pass (fp32 master + bf16 shadow).
 Non-2-D parameters go to `alternate_optimizer` if given, else to the SGD-momentum fallback
 (muon.py:119-138).  `betas/eps/weight_decay` are accepted and ignored, as in the reference (:41-52).
+
+Data parallel (`shard_ns=True`, set by the trainer when world > 1): gradients are already
+all-reduced, so every rank holds the same momentum; each rank then orthogonalises only its slice
+of every shape group (owner computes) and the results are exchanged with one in-place all-gather
+per group (a broadcast for groups with fewer matrices than ranks), issued asynchronously so the
+gather of group g overlaps the Newton-Schulz GEMMs of group g+1.  Communication volume equals
+the gradient all-reduce's all-gather half; Newton-Schulz work per rank drops by ~1/world
+(SURVEY 8e "fused mode", modal/modal_cuda_utils.py:468-490 for the size-balanced ownership idea).
 """
 from __future__ import annotations
 
@@ -19,6 +27,7 @@ from typing import Callable, Dict, Optional, Tuple, Union
 import torch
 
 from .. import ops
+from ..distributed import dp
 from ..flat import ParamStore, get_store
 
 
@@ -36,6 +45,7 @@ class Muon:
         self.count = 0
         self.grad_scale = 1.0        # e.g. 1/world_size for the data-parallel mean
         self.use_accumulated = False  # read gradients from store.acc (fp32) instead of store.grad
+        self.shard_ns = False         # owner-computes Newton-Schulz across data-parallel ranks
         self._store: Optional[ParamStore] = None
         self._buf = None
 
@@ -65,6 +75,7 @@ class Muon:
                         for g in store.mat_groups), default=0)
         self._u = torch.empty(max(max_numel, 8), dtype=torch.bfloat16, device=dev)
         self._x = torch.empty(max(max_numel, 8), dtype=torch.bfloat16, device=dev)
+        self._xg = None  # per-group gather buffers of the sharded mode (allocated on first use)
         self._ws = torch.empty(max(ws_bytes, 256), dtype=torch.uint8, device=dev)
         self._ss = torch.empty(max_batch, dtype=torch.float32, device=dev)
         self._inv = torch.empty(max_batch, dtype=torch.float32, device=dev)
@@ -91,29 +102,54 @@ class Muon:
         lib = ops.lib()
         stream = ops._stream()
         a, b, c = ops.NS_COEFFS
-        for g in store.mat_groups:
+        world = dp.world_size() if self.shard_ns else 1
+        rank = dp.env_rank_world()[0] if world > 1 else 0
+        if world > 1 and self._xg is None:
+            # one padded buffer per group: world * ceil(batch/world) matrices, so gathers can stay in flight
+            self._xg = [torch.empty(max(g.batch, world * dp.chunk_ranges(g.batch, world)[0]) * g.rows * g.cols,
+                                    dtype=torch.bfloat16, device=store.device) for g in store.mat_groups]
+        pending = []
+        for gi, g in enumerate(store.mat_groups):
             n = g.numel
+            rc = g.rows * g.cols
             gg = gsrc[g.offset:g.offset + n]
             buf = self._buf[g.offset:g.offset + n]
             u = self._u[:n]
-            x = self._x[:n]
+            x = self._x[:n] if world == 1 else self._xg[gi]
             ops.check(lib.b200_muon_momentum(gg.data_ptr(), ops._is_bf16(gg, "grad"), buf.data_ptr(),
-                                             u.data_ptr(), self._ss.data_ptr(), g.rows * g.cols, g.batch,
+                                             u.data_ptr(), self._ss.data_ptr(), rc, g.batch,
                                              float(self.momentum), int(self.nesterov),
                                              float(self.grad_scale), stream), "b200_muon_momentum")
             ops.check(lib.b200_ns_scales(self._ss.data_ptr(), self._inv.data_ptr(), self._inv2.data_ptr(),
                                          g.batch, ops.NS_EPS, stream), "b200_ns_scales")
+            mine = self.owned_ranges(g.batch, world, rank)   # matrices this rank orthogonalises
+            chunk = dp.chunk_ranges(g.batch, world)[0]
             tok = ops._t0("newton_schulz")
-            ops.check(lib.b200_newton_schulz(u.data_ptr(), x.data_ptr(), g.batch, g.rows, g.cols,
-                                             self.ns_steps, a, b, c, self._inv.data_ptr(),
-                                             self._inv2.data_ptr(), self._ws.data_ptr(), self._ws.numel(),
-                                             stream), "b200_newton_schulz")
+            for lo, hi in mine:
+                if hi <= lo:
+                    continue
+                ops.check(lib.b200_newton_schulz(u.data_ptr() + 2 * lo * rc, x.data_ptr() + 2 * lo * rc, hi - lo,
+                                                 g.rows, g.cols, self.ns_steps, a, b, c,
+                                                 self._inv.data_ptr() + 4 * lo, self._inv2.data_ptr() + 4 * lo,
+                                                 self._ws.data_ptr(), self._ws.numel(), stream),
+                          "b200_newton_schulz")
             ops._t1(tok)
-            scaling = max(1.0, g.rows / g.cols) ** 0.5
-            p32 = store.master[g.offset:g.offset + n]
-            p16 = store.shadow[g.offset:g.offset + n] if store.mixed else None
-            ops.check(lib.b200_axpy_update(p32.data_ptr(), ops._ptr(p16), x.data_ptr(), 1, n,
-                                           float(-lr * scaling), stream), "b200_axpy_update")
+            works = []
+            if world > 1:
+                if g.batch >= world:
+                    works.append(dp.all_gather_chunks_(x, chunk * rc, async_op=True))
+                else:
+                    works += [dp.broadcast_async_(x[i * rc:(i + 1) * rc], dp.small_group_owner(i, world))
+                              for i in range(g.batch)]
+            pending.append((g, x, works))
+            if world == 1:
+                self._apply(store, g, x, lr, lib, stream)   # the single x buffer is reused by the next group
+                pending.pop()
+        for g, x, works in pending:
+            for w in works:
+                if w is not None:
+                    w.wait()   # orders the current stream after the collective
+            self._apply(store, g, x, lr, lib, stream)
         if store.vec_end > store.vec_offset:
             lo, hi = store.vec_offset, store.vec_end
             if self.alternate_optimizer is not None:
@@ -123,6 +159,25 @@ class Muon:
                 ops.sgd_momentum(store.master[lo:hi], p16, gsrc[lo:hi], self._buf[lo:hi], self.momentum,
                                  self.nesterov, lr, self.grad_scale)
         self.count += 1
+
+    @staticmethod
+    def owned_ranges(batch: int, world: int, rank: int):
+        """[lo, hi) matrix ranges of a shape group that `rank` orthogonalises in the sharded mode."""
+        if world <= 1:
+            return [(0, batch)]
+        if batch >= world:
+            return [dp.chunk_ranges(batch, world)[1][rank]]
+        return [(i, i + 1) for i in range(batch) if dp.small_group_owner(i, world) == rank]
+
+    @staticmethod
+    def _apply(store, g, x, lr, lib, stream) -> None:
+        """p += -lr * max(1, rows/cols)^0.5 * X  (muon.py:111-114), fp32 master + bf16 shadow in one pass."""
+        n = g.numel
+        scaling = max(1.0, g.rows / g.cols) ** 0.5
+        p32 = store.master[g.offset:g.offset + n]
+        p16 = store.shadow[g.offset:g.offset + n] if store.mixed else None
+        ops.check(lib.b200_axpy_update(p32.data_ptr(), ops._ptr(p16), x.data_ptr(), 1, n,
+                                       float(-lr * scaling), stream), "b200_axpy_update")
 
     # MLX-style aliases kept so callers written against mlx.optimizers.Optimizer keep working
     def apply_gradients(self, gradients, model):

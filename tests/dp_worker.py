@@ -1,5 +1,5 @@
 """torchrun worker for the 2-GPU data-parallel test: one Muon update, rank r on synthetic batch
-(step 0, rank r); rank 0 saves the fp32 master weights."""
+(step 0, rank r); every rank saves its fp32 master weights."""
 import sys
 from pathlib import Path
 
@@ -22,8 +22,8 @@ def main():
     assert tr.distributed and tr.world == 2
     tr.train_step(0)
     torch.cuda.synchronize()
-    if tr.rank == 0:
-        torch.save({n: t.detach().cpu() for n, t in tr.store.named_master().items()}, out / "dp_rank0.pt")
+    assert getattr(tr.optimizer, "shard_ns", False), "owner-computes Newton-Schulz should be on under DP"
+    torch.save({n: t.detach().cpu() for n, t in tr.store.named_master().items()}, out / f"dp_rank{tr.rank}.pt")
     dp.barrier()
     dp.destroy()
 

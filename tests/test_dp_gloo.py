@@ -38,7 +38,19 @@ def _worker(rank: int, world: int, port: int, out_dir: str):
     mean = store.grad / world
     loss_tok = torch.tensor([(1.0 + rank) * (10 + 20 * rank), 10.0 + 20 * rank])
     loss = dp.token_weighted_loss(loss_tok)
-    torch.save({"master": ref, "local": local, "mean": mean, "loss": loss}, f"{out_dir}/r{rank}.pt")
+    # owner-computes exchange (Muon's sharded Newton-Schulz): 5 "matrices" of 6 elements, chunk = 3 per rank;
+    # each rank fills only the slice it owns, the in-place gather completes the buffer everywhere
+    chunk, ranges = dp.chunk_ranges(5, world)
+    xg = torch.full((world * chunk * 6,), -1.0)
+    lo, hi = ranges[rank]
+    xg[lo * 6:hi * 6] = torch.arange(lo * 6, hi * 6, dtype=torch.float32)
+    w = dp.all_gather_chunks_(xg, chunk * 6, async_op=True)
+    w.wait()
+    small = torch.full((4,), float(rank))
+    bw = dp.broadcast_async_(small, dp.small_group_owner(0, world))
+    bw.wait()
+    torch.save({"master": ref, "local": local, "mean": mean, "loss": loss, "gathered": xg[:30], "small": small},
+               f"{out_dir}/r{rank}.pt")
     dp.barrier()
     dp.destroy()
 
@@ -54,3 +66,22 @@ def test_two_rank_gradient_mean_and_loss(tmp_path):
     assert torch.equal(r0["mean"], r1["mean"])
     assert abs(r0["loss"] - R.token_weighted_loss([1.0, 2.0], [10, 30])) < 1e-6
     assert r0["loss"] == r1["loss"]
+    for r in (r0, r1):
+        assert torch.equal(r["gathered"], torch.arange(30, dtype=torch.float32))
+        assert torch.equal(r["small"], torch.full((4,), 1.0))           # lone matrix lives on the last rank
+
+
+def test_owner_partition_covers_every_matrix_once():
+    sys.path.insert(0, str(ROOT))
+    from mlx_cuda_distributed_pretraining_b200.distributed import dp
+    for world in (2, 3, 4, 8):
+        for batch in (1, 2, 5, 8, 12, 24, 25):
+            if batch >= world:
+                c, ranges = dp.chunk_ranges(batch, world)
+                assert c * world >= batch and len(ranges) == world
+                owned = [i for lo, hi in ranges for i in range(lo, hi)]
+                assert all(hi - lo <= c for lo, hi in ranges)
+            else:
+                owned = sorted(i for r in range(world) for i in range(batch) if dp.small_group_owner(i, world) == r)
+                assert dp.small_group_owner(0, world) == world - 1
+            assert owned == list(range(batch))

@@ -231,6 +231,10 @@ def test_two_gpu_data_parallel_matches_mean_of_gradients(tmp_path):
            "127.0.0.1", "--master-port", "29611", str(ROOT / "tests" / "dp_worker.py"), str(out)]
     subprocess.run(cmd, check=True, env=env, timeout=600)
     dpw = torch.load(out / "dp_rank0.pt")
+    dpw1 = torch.load(out / "dp_rank1.pt")
+    # owner-computes Newton-Schulz: every matrix is orthogonalised on one rank and gathered, so the
+    # replicas stay bit-identical
+    assert all(torch.equal(dpw[n], dpw1[n]) for n in dpw)
     tr = make_trainer(tmp_path, optimizer="muon", hp__gradient_accumulation_steps=2)
     for micro, rank in enumerate((0, 1)):
         tr.train_step(micro, R.synthetic_batch(0, rank, 2, 128, 256))
