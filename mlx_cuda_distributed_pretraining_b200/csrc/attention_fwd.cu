@@ -5,14 +5,17 @@
 // tiled with an online softmax, so the [B,H,S,S] score tensor the reference materialises (:134)
 // never exists.  Also emits LSE = log sum exp(scaled masked scores) for the backward pass.
 //
-// One CTA per (128-query tile, head, batch); 320 threads:
-//   warp 0      TMA producer: Q once, then K/V tiles (128 keys) through a 2-stage ring
-//   warp 1      tcgen05.mma issuer: S = Q K^T -> TMEM (double-buffered), O += P V -> TMEM
+// One CTA per (128-query tile, head, batch); 320 threads; at head_dim 64 TWO CTAs share an SM (97 KB smem,
+// 256 TMEM columns, <= 102 registers each) so one CTA's prologue / softmax / epilogue hides behind the
+// other's tensor work -- with S = 1024 a CTA lives for only 1..8 key tiles and its fixed costs matter:
+//   warp 0      TMA producer: Q once, then K tiles (128 keys) through a 2-stage ring, V single-buffered
+//   warp 1      tcgen05.mma issuer: S = Q K^T -> TMEM, O += P V -> TMEM
 //   warps 2-9   softmax, two warpgroups: each thread owns one query row (TMEM lane) x 64 of the 128
 //               key columns; scores stay in registers between row max (exchanged through smem) and
 //               exp2; P written to smem as a K-major 128B-swizzled bf16 operand; O rescaled in TMEM
 //               only when a row max moved.
-// S(j+1) is issued before P(j) is waited for, so QK^T of the next tile overlaps the softmax.
+// The S accumulator is handed back as soon as the scores sit in registers, so QK^T(j+1) overlaps the
+// exponentials of tile j even with a single S buffer.
 #include "common.cuh"
 #include "host.h"
 
@@ -32,13 +35,13 @@ struct FwdCfg {
   static constexpr int OFF_Q = 0;
   static constexpr int OFF_K = OFF_Q + TILE_BYTES;
   static constexpr int OFF_V = OFF_K + KV_STAGES * TILE_BYTES;
-  static constexpr int OFF_P = OFF_V + KV_STAGES * TILE_BYTES;
+  static constexpr int OFF_P = OFF_V + TILE_BYTES;  // V single-buffered: its reload hides behind the next softmax
   static constexpr int OFF_BAR = OFF_P + P_BYTES;
   static constexpr int OFF_RED = OFF_BAR + 256;  // [2][2][128] row-max exchange + [2][128] row-sum exchange
-  // >113.5 KB of smem also pins one CTA per SM, so the 512-column TMEM allocation never contends
-  static constexpr int SMEM_BYTES = (OFF_RED + 3072 + 1024) > 120 * 1024 ? (OFF_RED + 3072 + 1024) : 120 * 1024;
-  static constexpr int TMEM_COLS = 512;
-  static constexpr int TM_S0 = 0, TM_S1 = 128, TM_O = 256;
+  static constexpr int SMEM_BYTES = OFF_RED + 3072 + 1024;
+  static constexpr int CTAS_PER_SM = (2 * SMEM_BYTES + 2048 <= 227 * 1024) ? 2 : 1;
+  static constexpr int TMEM_COLS = 256;  // S 128 + O <= 128; two co-resident CTAs fill the 512 columns
+  static constexpr int TM_S = 0, TM_O = 128;
 };
 
 struct FwdArgs {
@@ -56,7 +59,7 @@ __device__ __forceinline__ float fast_exp2(float x) {
 }
 
 template <int D>
-__global__ void __launch_bounds__(FWD_THREADS, 1)
+__global__ void __launch_bounds__(FWD_THREADS, FwdCfg<D>::CTAS_PER_SM)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const FwdArgs p) {
   using Cfg = FwdCfg<D>;
@@ -65,15 +68,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const uint32_t sQ = sbase + Cfg::OFF_Q;
   const uint32_t sP = sbase + Cfg::OFF_P;
   auto sK = [&](int st) { return sbase + Cfg::OFF_K + st * Cfg::TILE_BYTES; };
-  auto sV = [&](int st) { return sbase + Cfg::OFF_V + st * Cfg::TILE_BYTES; };
+  const uint32_t sV = sbase + Cfg::OFF_V;
   const uint32_t bar = sbase + Cfg::OFF_BAR;
   const uint32_t q_full = bar;
   auto k_full = [&](int s) { return bar + 8u * (1 + s); };
   auto k_empty = [&](int s) { return bar + 8u * (3 + s); };
-  auto v_full = [&](int s) { return bar + 8u * (5 + s); };
-  auto v_empty = [&](int s) { return bar + 8u * (7 + s); };
-  auto s_full = [&](int s) { return bar + 8u * (9 + s); };
-  auto s_empty = [&](int s) { return bar + 8u * (11 + s); };
+  const uint32_t v_full = bar + 8u * 5;
+  const uint32_t v_empty = bar + 8u * 6;
+  const uint32_t s_full = bar + 8u * 9;
+  const uint32_t s_empty = bar + 8u * 10;
   const uint32_t p_full = bar + 8u * 13;
   const uint32_t pv_done = bar + 8u * 14;
   const uint32_t tmem_slot = bar + 8u * 15;
@@ -100,11 +103,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     for (int s = 0; s < 2; ++s) {
       mbar_init(k_full(s), 1);
       mbar_init(k_empty(s), 1);
-      mbar_init(v_full(s), 1);
-      mbar_init(v_empty(s), 1);
-      mbar_init(s_full(s), 1);
-      mbar_init(s_empty(s), 8);
     }
+    mbar_init(v_full, 1);
+    mbar_init(v_empty, 1);
+    mbar_init(s_full, 1);
+    mbar_init(s_empty, 8);
     mbar_init(p_full, 8);
     mbar_init(pv_done, 1);
     fence_mbar_init();
@@ -130,11 +133,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
         for (int db = 0; db < D / 64; ++db)
           tma_load_4d(sK(st) + db * 16384, &tmK, k_full(st), db * 64, hk, j * ATT_BKV, b);
-        mbar_wait(v_empty(st), ph ^ 1u);
-        mbar_arrive_expect_tx(v_full(st), Cfg::TILE_BYTES);
+        mbar_wait(v_empty, (j & 1u) ^ 1u);
+        mbar_arrive_expect_tx(v_full, Cfg::TILE_BYTES);
 #pragma unroll
         for (int db = 0; db < D / 64; ++db)
-          tma_load_4d(sV(st) + db * 16384, &tmV, v_full(st), db * 64, hk, j * ATT_BKV, b);
+          tma_load_4d(sV + db * 16384, &tmV, v_full, db * 64, hk, j * ATT_BKV, b);
       }
     }
   } else if (warp == 1) {
@@ -143,12 +146,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, false, false);
       constexpr uint32_t idesc_pv = make_idesc_bf16(128, D, false, true);
       auto issue_s = [&](int j) {
-        const int st = j & 1, sb = j & 1;
+        const int st = j & 1;
         const uint32_t ph = (j >> 1) & 1u;
-        mbar_wait(s_empty(sb), ph ^ 1u);
+        mbar_wait(s_empty, (j & 1u) ^ 1u);
         mbar_wait(k_full(st), ph);
         tc_fence_after_sync();
-        const uint32_t d_tmem = tmem_base + (sb ? Cfg::TM_S1 : Cfg::TM_S0);
+        const uint32_t d_tmem = tmem_base + Cfg::TM_S;
         if (elect_one()) {
 #pragma unroll
           for (int kk = 0; kk < D / 16; ++kk) {
@@ -157,7 +160,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                          make_smem_desc_sw128(sK(st) + off, 0, 1024), idesc_s, kk != 0);
           }
           umma_commit(k_empty(st));
-          umma_commit(s_full(sb));
+          umma_commit(s_full);
         }
         __syncwarp();
       };
@@ -165,18 +168,17 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       issue_s(0);
       for (int j = 0; j < n_kv; ++j) {
         if (j + 1 < n_kv) issue_s(j + 1);
-        const int st = j & 1;
         mbar_wait(p_full, j & 1u);
-        mbar_wait(v_full(st), (j >> 1) & 1u);
+        mbar_wait(v_full, j & 1u);
         tc_fence_after_sync();
         if (elect_one()) {
 #pragma unroll
           for (int kk = 0; kk < ATT_BKV / 16; ++kk) {
             const uint64_t da = make_smem_desc_sw128(sP + (kk >> 2) * 16384 + (kk & 3) * 32, 0, 1024);
-            const uint64_t db = make_smem_desc_sw128(sV(st) + kk * 2048, 16384, 1024);
+            const uint64_t db = make_smem_desc_sw128(sV + kk * 2048, 16384, 1024);
             umma_bf16_ss(tmem_base + Cfg::TM_O, da, db, idesc_pv, (j | kk) != 0);
           }
-          umma_commit(v_empty(st));
+          umma_commit(v_empty);
           umma_commit(pv_done);
         }
         __syncwarp();
@@ -199,13 +201,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     float m = -INFINITY, l = 0.f;
 
     for (int j = 0; j < n_kv; ++j) {
-      const int sb = j & 1;
-      const uint32_t t_s = t_lane + (sb ? Cfg::TM_S1 : Cfg::TM_S0) + cbase;
+      const uint32_t t_s = t_lane + Cfg::TM_S + cbase;
       const int k0 = j * ATT_BKV + cbase;
       const bool need_mask = (p.causal && j * ATT_BKV + ATT_BKV - 1 > q0) || (j * ATT_BKV + ATT_BKV > p.S);
       const int kmax = p.causal ? (q_row < p.S - 1 ? q_row : p.S - 1) : p.S - 1;  // last valid key
 
-      mbar_wait(s_full(sb), (j >> 1) & 1u);
+      mbar_wait(s_full, j & 1u);
       tc_fence_after_sync();
       uint32_t v[64];
       tmem_ld_32x32b_x32(t_s, v);
@@ -214,7 +215,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       // the scores now live in registers: hand the S buffer back to the tensor core right away
       tc_fence_before_sync();
       __syncwarp();
-      if (lane == 0) mbar_arrive(s_empty(sb));
+      if (lane == 0) mbar_arrive(s_empty);
 
       float mx = -INFINITY;
       if (need_mask) {
@@ -240,14 +241,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         mbar_wait(pv_done, (j - 1) & 1u);
         tc_fence_after_sync();
         if (__any_sync(0xffffffffu, m_new > m)) {
+          // 8 columns at a time: the 64 scores stay live across this loop and the register budget with
+          // two CTAs per SM is 102
 #pragma unroll 1
-          for (int c0 = 0; c0 < OH; c0 += 32) {
-            uint32_t o[32];
-            tmem_ld_32x32b_x32(t_lane + Cfg::TM_O + wg * OH + c0, o);
+          for (int c0 = 0; c0 < OH; c0 += 8) {
+            uint32_t o[8];
+            tmem_ld_32x32b_x8(t_lane + Cfg::TM_O + wg * OH + c0, o);
             tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            tmem_st_32x32b_x32(t_lane + Cfg::TM_O + wg * OH + c0, o);
+            for (int i = 0; i < 8; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st_32x32b_x8(t_lane + Cfg::TM_O + wg * OH + c0, o);
           }
           tmem_st_wait();
         }
