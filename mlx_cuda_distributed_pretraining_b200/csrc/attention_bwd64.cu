@@ -7,12 +7,19 @@
 // red.global = 32 L2 transactions per warp instruction).  This version
 //   * double-buffers the P^T / dS^T operand tiles, and issues S,dP(it+1) BEFORE dV,dK,dQ(it), so the
 //     softmax threads of iteration it+1 run while the tensor core finishes iteration it;
-//   * drains dQ(it-1) through an fp32 smem staging tile (aliasing the idle P^T buffer) and one bulk
-//     tensor reduce-add (cp.reduce.async.bulk.tensor .add) per 32-column box, so the L2 atomics run
-//     asynchronously instead of stalling the softmax threads on per-lane red.global traffic;
+//   * gives the dQ drain its own warpgroup (warps 10-13) and double-buffers dQ in TMEM: dQ(it) leaves
+//     through a swizzled fp32 staging tile (aliasing P^T[it & 1], idle between the MMAs of `it` and the
+//     softmax of `it + 2`; it is held only until the tile is back in registers) as coalesced
+//     red.global.add.v4.f32 -- every warp instruction covers two full 256-byte rows.  A stand-alone
+//     warpgroup sustains ~20 B/clk/SM this way (tools/microbench/red_pattern.cu: 1600 cycles per tile
+//     with all SMs active, 5.7 TB/s chip-wide, L2-resident accumulator), inside the softmax's 2400;
 //   * reads LSE / delta as 128-bit shared loads, prefetched one iteration ahead.
+// Tried and dropped (r01 traces): computing S^T/dP^T in two 64-query halves so that half A of tile it+1
+// is issued mid-softmax -- the extra operand re-reads slowed the softmax's own shared-memory stores more
+// than the overlap gained.  Shared-memory bandwidth is the co-bottleneck here: MMA operand reads
+// (~208 KB) + P^T/dS^T stores (64 KB) + dQ staging (64 KB) per iteration = ~2600 cycles at 128 B/clk.
 // smem: K 16 + V 16 + Q 2x16 + dO 2x16 + P^T 2x32 + dS^T 2x32 = 224 KB (+2 KB lse/delta + barriers).
-// TMEM: S^T 128 | dP^T 128 | dV 64 | dK 64 | dQ 64 columns.
+// TMEM: S^T 128 | dP^T 128 | dV 64 | dK 64 | dQ 2 x 64 columns.
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -22,7 +29,7 @@ namespace b200 {
 
 namespace {
 
-constexpr int B64_THREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2-9 two softmax warpgroups
+constexpr int B64_THREADS = 448;  // warp 0 TMA, warp 1 MMA, warps 2-9 two softmax warpgroups, 10-13 dQ drain
 constexpr int BT = 128;
 constexpr int D = 64;
 constexpr int TILE = 128 * D * 2;       // 16 KB
@@ -36,10 +43,7 @@ constexpr int OFF_DS = OFF_PT + 2 * PT_BYTES;
 constexpr int OFF_LSE = OFF_DS + 2 * PT_BYTES;  // [2 slots][lse 128 | delta 128] floats
 constexpr int OFF_BAR = OFF_LSE + 2 * 256 * 4;
 constexpr int SMEM_BYTES = OFF_BAR + 128;
-constexpr int TM_S = 0, TM_DP = 128, TM_DV = 256, TM_DK = 320, TM_DQ = 384;
-// dQ drain flavour: bulk tensor reduce-add (one instruction, asynchronous) vs coalesced red.global.v4.
-// Both are bound by L2 atomic throughput (~1 TB/s measured); the direct form measured 5 % faster.
-constexpr bool kTmaReduceDrain = false;
+constexpr int TM_S = 0, TM_DP = 128, TM_DV = 256, TM_DK = 320, TM_DQ = 384;  // dQ buffer b at TM_DQ + 64 b
 
 struct Bwd64Args {
   const float* lse;
@@ -79,7 +83,7 @@ __device__ __forceinline__ void st_tile_chunk(uint32_t tile, int row, int chunk,
 __global__ void __launch_bounds__(B64_THREADS, 1)
 attn_bwd64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                   const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
-                  const __grid_constant__ CUtensorMap tmDQ, const Bwd64Args p) {
+                  const Bwd64Args p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
   if ((sbase & 1023u) != 0) __trap();  // 128B-swizzled TMA/UMMA tiles need a 1 KB aligned base
@@ -95,9 +99,10 @@ attn_bwd64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   auto q_empty = [&](int s) { return bar + 8u * (3 + s); };
   const uint32_t s_full = bar + 8u * 5;
   const uint32_t pds_full = bar + 8u * 6;
-  const uint32_t dq_full = bar + 8u * 7;
-  const uint32_t dq_empty = bar + 8u * 8;
-  const uint32_t tmem_slot = bar + 8u * 9;
+  auto dq_full = [&](int s) { return bar + 8u * (7 + s); };
+  auto dq_empty = [&](int s) { return bar + 8u * (9 + s); };
+  auto stg_free = [&](int s) { return bar + 8u * (11 + s); };
+  const uint32_t tmem_slot = bar + 8u * 13;
 
   const int warp = warp_idx_uniform();
   const int lane = threadIdx.x & 31;
@@ -114,7 +119,6 @@ attn_bwd64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
     tma_prefetch_desc(&tmDO);
-    tma_prefetch_desc(&tmDQ);
   }
   if (warp == 1 && lane == 0) {
     mbar_init(kv_full, 1);
@@ -124,8 +128,11 @@ attn_bwd64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     }
     mbar_init(s_full, 1);
     mbar_init(pds_full, 8);
-    mbar_init(dq_full, 1);
-    mbar_init(dq_empty, 8);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(dq_full(s), 1);
+      mbar_init(dq_empty(s), 4);
+      mbar_init(stg_free(s), 4);
+    }
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, 512);
@@ -183,7 +190,7 @@ attn_bwd64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       if (lane == 0) T64(9);
       if (it + 1 < n_it) issue_s(it + 1);
       if (lane == 0) T64(10);
-      if (it > 0) mbar_wait(dq_empty, (it - 1) & 1u);  // dQ(it-1) left TMEM
+      if (it > 1) mbar_wait(dq_empty(bf), ((it - 2) >> 1) & 1u);  // dQ(it-2) left this TMEM buffer
       tc_fence_after_sync();
       if (lane == 0) T64(11);
       if (elect_one()) {
@@ -199,16 +206,66 @@ attn_bwd64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         // dQ = dS K  (M = queries, N = head dim, K = keys): dS^T tile read as an MN-major A operand
 #pragma unroll
         for (int kk = 0; kk < BT / 16; ++kk)
-          umma_bf16_ss(tmem_base + TM_DQ, make_smem_desc_sw128(sDS(bf) + kk * 2048, 16384, 1024),
+          umma_bf16_ss(tmem_base + TM_DQ + 64 * bf, make_smem_desc_sw128(sDS(bf) + kk * 2048, 16384, 1024),
                        make_smem_desc_sw128(sK + kk * 2048, 16384, 1024), idesc_dq, kk != 0);
         umma_commit(q_empty(st));
-        umma_commit(dq_full);
+        umma_commit(dq_full(bf));
       }
       __syncwarp();
       if (lane == 0) T64(12);
     }
+  } else if (warp >= 10) {
+    // ------------------------------------ dQ drain warpgroup --------------------------------------
+    const int qd = warp & 3;
+    const int row = qd * 32 + lane;  // query row of the dQ tile = TMEM lane
+    const int dt = threadIdx.x - 320;  // 0..127
+    const uint32_t t_lane = tmem_base + (uint32_t(qd * 32) << 16);
+    for (int it = 0; it < n_it; ++it) {
+      const int bf = it & 1;
+      const int h = hk * G + it / n_qt;
+      const int q0 = (qt_first + it % n_qt) * BT;
+      mbar_wait(dq_full(bf), (it >> 1) & 1u);  // every MMA of `it` retired: dQ ready, P^T[bf] idle
+      tc_fence_after_sync();
+      if (dt == 0) T64(13);
+      uint32_t v[64];
+      tmem_ld_32x32b_x32(t_lane + TM_DQ + 64 * bf, v);
+      tmem_ld_32x32b_x32(t_lane + TM_DQ + 64 * bf + 32, v + 32);
+      tmem_ld_wait();
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(dq_empty(bf));
+      // staging: [128 rows][16 chunks of 16 B], chunk ^= row & 15 (conflict-free both ways)
+      const uint32_t stg = sPT(bf);
+#pragma unroll
+      for (int ch = 0; ch < 16; ++ch) {
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + row * 256 + ((ch ^ (row & 15)) << 4)),
+                     "r"(v[ch * 4 + 0]), "r"(v[ch * 4 + 1]), "r"(v[ch * 4 + 2]), "r"(v[ch * 4 + 3])
+                     : "memory");
+      }
+      named_bar_sync(2, 128);
+      float4 val[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int c = dt + 128 * i;  // 16-byte chunk id: row = c / 16, chunk = c % 16
+        const int r = c >> 4, ch = c & 15;
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                     : "=f"(val[i].x), "=f"(val[i].y), "=f"(val[i].z), "=f"(val[i].w)
+                     : "r"(stg + r * 256 + ((ch ^ (r & 15)) << 4)));
+      }
+      // the tile is back in registers: hand P^T[bf] to the softmax of it + 2 before the slow part
+      __syncwarp();
+      if (lane == 0) mbar_arrive(stg_free(bf));
+      float* dst = p.dq_acc + (((long long)b * p.S + q0) * p.H + h) * D;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int c = dt + 128 * i;
+        const int r = c >> 4, ch = c & 15;
+        if (q0 + r < p.S) red_add_v4(dst + (long long)r * p.H * D + ch * 4, val[i]);
+      }
+      if (dt == 0) T64(14);
+    }
   } else {
-    // --------------------------- softmax / dQ drain / dK,dV epilogue ------------------------
+    // ------------------------------- softmax / dK,dV epilogue --------------------------------------
     const int qd = warp & 3;
     const int wg = (warp - 2) >> 2;
     const int row = qd * 32 + lane;  // key row (S^T) or query row (dQ)
@@ -237,62 +294,6 @@ attn_bwd64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         val = q < p.S ? val : 0.f;
       lse_s[(it & 1) * 256 + tid] = val;
     };
-    // dQ(it): TMEM -> fp32 staging tile in TMA layout (two [128 x 128 B] 128B-swizzled boxes, aliasing
-    // P^T[it & 1], idle once dq_full(it) fired) -> ONE bulk tensor reduce-add per box into dq_acc.  The
-    // threads only pay for the staging; the L2 atomics run asynchronously behind the next softmax.
-    auto drain_dq = [&](int it) {
-      const int h = hk * G + it / n_qt;
-      const int q0 = (qt_first + it % n_qt) * BT;
-      mbar_wait(dq_full, it & 1u);
-      tc_fence_after_sync();
-      uint32_t v[32];
-      tmem_ld_32x32b_x32(t_lane + TM_DQ + wg * 32, v);
-      tmem_ld_wait();
-      tc_fence_before_sync();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(dq_empty);
-      if constexpr (kTmaReduceDrain) {
-        const uint32_t stg = sPT(it & 1) + wg * 16384 + row * 128;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + ((j ^ (row & 7)) << 4)),
-                       "r"(v[j * 4 + 0]), "r"(v[j * 4 + 1]), "r"(v[j * 4 + 2]), "r"(v[j * 4 + 3])
-                       : "memory");
-        }
-        fence_proxy_async_smem();
-        named_bar_sync(1, 256);
-        if (tid == 0) {
-          tma_reduce_add_4d(&tmDQ, sPT(it & 1), 0, h, q0, b);
-          tma_reduce_add_4d(&tmDQ, sPT(it & 1) + 16384, 32, h, q0, b);
-          tma_commit_group();
-          tma_wait_group_read<0>();  // staging tile may be overwritten once the bulk op has read it
-        }
-      } else {
-        // [128 rows][16 chunks of 16 B], chunk ^= row & 15; then coalesced red.global.add.v4.f32: every
-        // warp instruction covers two contiguous 256-byte rows (4 lines instead of 32)
-        const uint32_t stg = sPT(it & 1);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int ch = wg * 8 + j;
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + row * 256 + ((ch ^ (row & 15)) << 4)),
-                       "r"(v[j * 4 + 0]), "r"(v[j * 4 + 1]), "r"(v[j * 4 + 2]), "r"(v[j * 4 + 3])
-                       : "memory");
-        }
-        named_bar_sync(1, 256);
-        float* dst = p.dq_acc + (((long long)b * p.S + q0) * p.H + h) * D;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int c = tid + 256 * i;  // 16-byte chunk id: row = c / 16, chunk = c % 16
-          const int r = c >> 4, ch = c & 15;
-          float4 val;
-          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                       : "=f"(val.x), "=f"(val.y), "=f"(val.z), "=f"(val.w)
-                       : "r"(stg + r * 256 + ((ch ^ (r & 15)) << 4)));
-          if (q0 + r < p.S) red_add_v4(dst + (long long)r * p.H * D + ch * 4, val);
-        }
-      }
-    };
-
     if (n_it > 0) put_lse(0, fetch_lse(0));
     named_bar_sync(1, 256);
     for (int it = 0; it < n_it; ++it) {
@@ -306,6 +307,7 @@ attn_bwd64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       if (it + 1 < n_it) lse_next = fetch_lse(it + 1);  // latency hides behind this iteration's softmax
       mbar_wait(s_full, it & 1u);
       tc_fence_after_sync();
+      if (it > 1) mbar_wait(stg_free(bf), ((it - 2) >> 1) & 1u);  // drain of it-2 no longer reads P^T[bf]
       if (threadIdx.x == 64) T64(1);
 #pragma unroll 1
       for (int c0 = cbase; c0 < cbase + 64; c0 += 32) {
@@ -343,18 +345,15 @@ attn_bwd64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 
       if (it + 1 < n_it) put_lse(it + 1, lse_next);  // visible after the barriers below, before softmax(it+1)
       if (threadIdx.x == 64) T64(3);
-      if (it > 0) drain_dq(it - 1);          // tensor core is busy with dV,dK,dQ(it) meanwhile
-      if (threadIdx.x == 64) T64(4);
-      named_bar_sync(1, 256);                // staging reads done before P^T[(it-1)&1] is rewritten
+      named_bar_sync(1, 256);  // lse/delta slot of it+1 complete before anyone reads it
       if (threadIdx.x == 64) T64(5);
     }
     if (n_it > 0) {
-      drain_dq(n_it - 1);
-      if (tid == 0) tma_wait_group<0>();  // all reduce-adds of this CTA have landed in dq_acc
-      named_bar_sync(1, 256);
+      mbar_wait(dq_full((n_it - 1) & 1), ((n_it - 1) >> 1) & 1u);  // the last commit covers every MMA before it
+      tc_fence_after_sync();
     }
 
-    // dK / dV (the last dq_full commit covers every MMA issued before it); column halves per warpgroup
+    // dK / dV; column halves per warpgroup
 #pragma unroll 1
     for (int which = 0; which < 2; ++which) {
       __nv_bfloat16* out = (which == 0 ? p.dv : p.dk) + (((long long)b * p.S + key) * p.Hk + hk) * D + wg * 32;
@@ -411,10 +410,8 @@ int launch_attn_bwd64(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUte
     const char* e = getenv("B200_ATTN_TRACE");
     a.trace = e ? reinterpret_cast<long long*>(strtoull(e, nullptr, 16)) : nullptr;
   }
-  CUtensorMap tmDQ;  // fp32 [B,S,H,64] accumulator, box {32, 1, 128, 1}
-  if (int rc = make_bshd_map(&tmDQ, dq_acc, B, S, H, D, BT, true)) return rc;
   dim3 grid((S + BT - 1) / BT, Hk, B);
-  attn_bwd64_kernel<<<grid, B64_THREADS, SMEM_BYTES, stream>>>(tmQ, tmK, tmV, tmDO, tmDQ, a);
+  attn_bwd64_kernel<<<grid, B64_THREADS, SMEM_BYTES, stream>>>(tmQ, tmK, tmV, tmDO, a);
   B200_CHECK_LAUNCH();
   return B200_OK;
 }

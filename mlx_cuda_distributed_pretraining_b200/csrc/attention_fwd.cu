@@ -8,12 +8,12 @@
 // One CTA per (128-query tile, head, batch); 320 threads; at head_dim 64 TWO CTAs share an SM (97 KB smem,
 // 256 TMEM columns, <= 102 registers each) so one CTA's prologue / softmax / epilogue hides behind the
 // other's tensor work -- with S = 1024 a CTA lives for only 1..8 key tiles and its fixed costs matter:
-//   warp 0      TMA producer: Q once, then K tiles (128 keys) through a 2-stage ring, V single-buffered
-//   warp 1      tcgen05.mma issuer: S = Q K^T -> TMEM, O += P V -> TMEM
+//   warp 0      TMA producer: Q once, then K / V tiles (128 keys) through 2-stage rings
+//   warp 1      tcgen05.mma issuer: S = Q K^T -> TMEM, O += P V -> TMEM with P as a TMEM A operand
 //   warps 2-9   softmax, two warpgroups: each thread owns one query row (TMEM lane) x 64 of the 128
 //               key columns; scores stay in registers between row max (exchanged through smem) and
-//               exp2; P written to smem as a K-major 128B-swizzled bf16 operand; O rescaled in TMEM
-//               only when a row max moved.
+//               exp2; P written back to TMEM as packed bf16 (tcgen05.st); O rescaled in TMEM only when a
+//               row max moved.
 // The S accumulator is handed back as soon as the scores sit in registers, so QK^T(j+1) overlaps the
 // exponentials of tile j even with a single S buffer.
 #include "common.cuh"
@@ -27,21 +27,27 @@ constexpr int ATT_BQ = 128;
 constexpr int ATT_BKV = 128;
 constexpr int FWD_THREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2-9: two softmax warpgroups
 constexpr int KV_STAGES = 2;
+// P = exp(S - max) goes back to TENSOR MEMORY (packed bf16, 64 columns) and feeds O += P V as the A operand
+// of tcgen05.mma (A in TMEM, B = V in smem): no 32 KB smem round trip per key tile, and the MMA reads only V
+// from shared memory.  false = the first version (P as a swizzled K-major smem tile).
+constexpr bool kPInTmem = true;
 
 template <int D>
 struct FwdCfg {
   static constexpr int TILE_BYTES = 128 * D * 2;  // one Q / K / V tile
-  static constexpr int P_BYTES = 128 * 128 * 2;
+  static constexpr int P_BYTES = kPInTmem ? 0 : 128 * 128 * 2;
+  static constexpr int V_STAGES = kPInTmem ? 2 : 1;  // without the smem P tile both K and V are double-buffered
   static constexpr int OFF_Q = 0;
   static constexpr int OFF_K = OFF_Q + TILE_BYTES;
   static constexpr int OFF_V = OFF_K + KV_STAGES * TILE_BYTES;
-  static constexpr int OFF_P = OFF_V + TILE_BYTES;  // V single-buffered: its reload hides behind the next softmax
+  static constexpr int OFF_P = OFF_V + V_STAGES * TILE_BYTES;
   static constexpr int OFF_BAR = OFF_P + P_BYTES;
   static constexpr int OFF_RED = OFF_BAR + 256;  // [2][2][128] row-max exchange + [2][128] row-sum exchange
   static constexpr int SMEM_BYTES = OFF_RED + 3072 + 1024;
   static constexpr int CTAS_PER_SM = (2 * SMEM_BYTES + 2048 <= 227 * 1024) ? 2 : 1;
-  static constexpr int TMEM_COLS = 256;  // S 128 + O <= 128; two co-resident CTAs fill the 512 columns
-  static constexpr int TM_S = 0, TM_O = 128;
+  // S 128 | O D | P 64 (packed bf16): 256 columns at D = 64, so two co-resident CTAs fill the 512
+  static constexpr int TMEM_COLS = (128 + D + 64 <= 256) ? 256 : 512;
+  static constexpr int TM_S = 0, TM_O = 128, TM_P = 128 + D;
 };
 
 struct FwdArgs {
@@ -68,13 +74,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const uint32_t sQ = sbase + Cfg::OFF_Q;
   const uint32_t sP = sbase + Cfg::OFF_P;
   auto sK = [&](int st) { return sbase + Cfg::OFF_K + st * Cfg::TILE_BYTES; };
-  const uint32_t sV = sbase + Cfg::OFF_V;
+  auto sV = [&](int j) { return sbase + Cfg::OFF_V + (Cfg::V_STAGES == 2 ? (j & 1) : 0) * Cfg::TILE_BYTES; };
   const uint32_t bar = sbase + Cfg::OFF_BAR;
   const uint32_t q_full = bar;
   auto k_full = [&](int s) { return bar + 8u * (1 + s); };
   auto k_empty = [&](int s) { return bar + 8u * (3 + s); };
-  const uint32_t v_full = bar + 8u * 5;
-  const uint32_t v_empty = bar + 8u * 6;
+  // V tile j lives in stage j % V_STAGES; its barriers complete once per V_STAGES tiles
+  auto v_full = [&](int j) { return bar + 8u * (5 + (Cfg::V_STAGES == 2 ? (j & 1) : 0)); };
+  auto v_empty = [&](int j) { return bar + 8u * (7 + (Cfg::V_STAGES == 2 ? (j & 1) : 0)); };
+  auto v_par = [&](int j) { return (uint32_t)((Cfg::V_STAGES == 2 ? (j >> 1) : j) & 1); };
   const uint32_t s_full = bar + 8u * 9;
   const uint32_t s_empty = bar + 8u * 10;
   const uint32_t p_full = bar + 8u * 13;
@@ -104,8 +112,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_init(k_full(s), 1);
       mbar_init(k_empty(s), 1);
     }
-    mbar_init(v_full, 1);
-    mbar_init(v_empty, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(v_full(s), 1);
+      mbar_init(v_empty(s), 1);
+    }
     mbar_init(s_full, 1);
     mbar_init(s_empty, 8);
     mbar_init(p_full, 8);
@@ -133,11 +143,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
         for (int db = 0; db < D / 64; ++db)
           tma_load_4d(sK(st) + db * 16384, &tmK, k_full(st), db * 64, hk, j * ATT_BKV, b);
-        mbar_wait(v_empty, (j & 1u) ^ 1u);
-        mbar_arrive_expect_tx(v_full, Cfg::TILE_BYTES);
+        mbar_wait(v_empty(j), v_par(j) ^ 1u);
+        mbar_arrive_expect_tx(v_full(j), Cfg::TILE_BYTES);
 #pragma unroll
         for (int db = 0; db < D / 64; ++db)
-          tma_load_4d(sV + db * 16384, &tmV, v_full, db * 64, hk, j * ATT_BKV, b);
+          tma_load_4d(sV(j) + db * 16384, &tmV, v_full(j), db * 64, hk, j * ATT_BKV, b);
       }
     }
   } else if (warp == 1) {
@@ -169,16 +179,21 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       for (int j = 0; j < n_kv; ++j) {
         if (j + 1 < n_kv) issue_s(j + 1);
         mbar_wait(p_full, j & 1u);
-        mbar_wait(v_full, j & 1u);
+        mbar_wait(v_full(j), v_par(j));
         tc_fence_after_sync();
         if (elect_one()) {
 #pragma unroll
           for (int kk = 0; kk < ATT_BKV / 16; ++kk) {
-            const uint64_t da = make_smem_desc_sw128(sP + (kk >> 2) * 16384 + (kk & 3) * 32, 0, 1024);
-            const uint64_t db = make_smem_desc_sw128(sV + kk * 2048, 16384, 1024);
-            umma_bf16_ss(tmem_base + Cfg::TM_O, da, db, idesc_pv, (j | kk) != 0);
+            const uint64_t db = make_smem_desc_sw128(sV(j) + kk * 2048, 16384, 1024);
+            if constexpr (kPInTmem) {
+              // A = P[128 x 16] from TMEM: 16 bf16 of K per row = 8 packed columns per K step
+              umma_bf16_ts(tmem_base + Cfg::TM_O, tmem_base + Cfg::TM_P + kk * 8, db, idesc_pv, (j | kk) != 0);
+            } else {
+              const uint64_t da = make_smem_desc_sw128(sP + (kk >> 2) * 16384 + (kk & 3) * 32, 0, 1024);
+              umma_bf16_ss(tmem_base + Cfg::TM_O, da, db, idesc_pv, (j | kk) != 0);
+            }
           }
-          umma_commit(v_empty);
+          umma_commit(v_empty(j));
           umma_commit(pv_done);
         }
         __syncwarp();
@@ -257,25 +272,42 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
       // probabilities -> bf16 P tile (K-major, 128B swizzle): this warpgroup fills 64-column block `wg`
       float rs = 0.f;
-      const uint32_t blk = sP + wg * 16384 + row * 128;
+      if constexpr (kPInTmem) {
+        // this warpgroup's 64 key columns = packed columns [32 wg, 32 wg + 32) of the P operand
 #pragma unroll
-      for (int g = 0; g < 8; ++g) {
-        float e[8];
+        for (int hlf = 0; hlf < 2; ++hlf) {
+          uint32_t pk[16];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          e[i] = fast_exp2(fmaf(__uint_as_float(v[g * 8 + i]), sl2, -mb));
-          rs += e[i];
+          for (int i = 0; i < 16; ++i) {
+            const float e0 = fast_exp2(fmaf(__uint_as_float(v[hlf * 32 + 2 * i]), sl2, -mb));
+            const float e1 = fast_exp2(fmaf(__uint_as_float(v[hlf * 32 + 2 * i + 1]), sl2, -mb));
+            rs += e0 + e1;
+            pk[i] = pack_bf16x2(e0, e1);
+          }
+          tmem_st_32x32b_x16(t_lane + Cfg::TM_P + wg * 32 + hlf * 16, pk);
         }
-        const uint32_t addr = blk + ((g ^ (row & 7)) << 4);
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pack_bf16x2(e[0], e[1])),
-                     "r"(pack_bf16x2(e[2], e[3])), "r"(pack_bf16x2(e[4], e[5])), "r"(pack_bf16x2(e[6], e[7]))
-                     : "memory");
+        tmem_st_wait();
+      } else {
+        const uint32_t blk = sP + wg * 16384 + row * 128;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          float e[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            e[i] = fast_exp2(fmaf(__uint_as_float(v[g * 8 + i]), sl2, -mb));
+            rs += e[i];
+          }
+          const uint32_t addr = blk + ((g ^ (row & 7)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pack_bf16x2(e[0], e[1])),
+                       "r"(pack_bf16x2(e[2], e[3])), "r"(pack_bf16x2(e[4], e[5])), "r"(pack_bf16x2(e[6], e[7]))
+                       : "memory");
+        }
+        fence_proxy_async_smem();
       }
       l = l * alpha + rs;
       m = m_new;
-      // publish: P tile + rescaled O visible to the tensor core (async proxy)
+      // publish: P + rescaled O visible to the tensor core
       tc_fence_before_sync();
-      fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);
     }
