@@ -7,10 +7,11 @@
 // red.global = 32 L2 transactions per warp instruction).  This version
 //   * double-buffers the P^T / dS^T operand tiles, and issues S,dP(it+1) BEFORE dV,dK,dQ(it), so the
 //     softmax threads of iteration it+1 run while the tensor core finishes iteration it;
-//   * gives the dQ drain its own warpgroup (warps 10-13) and double-buffers dQ in TMEM: dQ(it) leaves
-//     through a swizzled fp32 staging tile (aliasing P^T[it & 1], idle between the MMAs of `it` and the
-//     softmax of `it + 2`; it is held only until the tile is back in registers) as coalesced
-//     red.global.add.v4.f32 -- every warp instruction covers two full 256-byte rows.  A stand-alone
+//   * keeps P^T in TENSOR MEMORY (packed bf16, 64 columns, written with tcgen05.st) and feeds dV += P^T dO
+//     with it as a TMEM A operand: 64 KB less shared-memory traffic per iteration, and the 64 KB of smem the
+//     two P^T tiles occupied now hold a third Q/dO stage and a dedicated dQ staging tile;
+//   * gives the dQ drain its own warpgroup (warps 10-13): dQ(it) leaves through a swizzled fp32 staging
+//     tile as coalesced red.global.add.v4.f32 -- every warp instruction covers two full 256-byte rows.  A stand-alone
 //     warpgroup sustains ~20 B/clk/SM this way (tools/microbench/red_pattern.cu: 1600 cycles per tile
 //     with all SMs active, 5.7 TB/s chip-wide, L2-resident accumulator), inside the softmax's 2400;
 //   * reads LSE / delta as 128-bit shared loads, prefetched one iteration ahead.
@@ -18,8 +19,8 @@
 // is issued mid-softmax -- the extra operand re-reads slowed the softmax's own shared-memory stores more
 // than the overlap gained.  Shared-memory bandwidth is the co-bottleneck here: MMA operand reads
 // (~208 KB) + P^T/dS^T stores (64 KB) + dQ staging (64 KB) per iteration = ~2600 cycles at 128 B/clk.
-// smem: K 16 + V 16 + Q 2x16 + dO 2x16 + P^T 2x32 + dS^T 2x32 = 224 KB (+2 KB lse/delta + barriers).
-// TMEM: S^T 128 | dP^T 128 | dV 64 | dK 64 | dQ 2 x 64 columns.
+// smem: K 16 + V 16 + Q 3x16 + dO 3x16 + dS^T 2x32 + dQ staging 32 = 224 KB (+2 KB lse/delta + barriers).
+// TMEM: S^T 128 | dP^T 128 | dV 64 | dK 64 | dQ 64 | P^T 64 (packed bf16) columns.
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -36,14 +37,15 @@ constexpr int TILE = 128 * D * 2;       // 16 KB
 constexpr int PT_BYTES = 128 * 128 * 2;  // 32 KB
 constexpr int OFF_K = 0;
 constexpr int OFF_V = OFF_K + TILE;
-constexpr int OFF_Q = OFF_V + TILE;        // 2 stages
-constexpr int OFF_DO = OFF_Q + 2 * TILE;   // 2 stages
-constexpr int OFF_PT = OFF_DO + 2 * TILE;  // 2 buffers
-constexpr int OFF_DS = OFF_PT + 2 * PT_BYTES;
+constexpr int QS = 3;                       // Q / dO stages
+constexpr int OFF_Q = OFF_V + TILE;
+constexpr int OFF_DO = OFF_Q + QS * TILE;
+constexpr int OFF_STG = OFF_DO + QS * TILE;  // fp32 dQ staging tile of the drain warpgroup
+constexpr int OFF_DS = OFF_STG + PT_BYTES;   // 2 buffers
 constexpr int OFF_LSE = OFF_DS + 2 * PT_BYTES;  // [2 slots][lse 128 | delta 128] floats
 constexpr int OFF_BAR = OFF_LSE + 2 * 256 * 4;
-constexpr int SMEM_BYTES = OFF_BAR + 128;
-constexpr int TM_S = 0, TM_DP = 128, TM_DV = 256, TM_DK = 320, TM_DQ = 384;  // dQ buffer b at TM_DQ + 64 b
+constexpr int SMEM_BYTES = OFF_BAR + 192;
+constexpr int TM_S = 0, TM_DP = 128, TM_DV = 256, TM_DK = 320, TM_DQ = 384, TM_PT = 448;
 
 struct Bwd64Args {
   const float* lse;
@@ -90,18 +92,19 @@ attn_bwd64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   const uint32_t sK = sbase + OFF_K, sV = sbase + OFF_V;
   auto sQ = [&](int st) { return sbase + OFF_Q + st * TILE; };
   auto sDO = [&](int st) { return sbase + OFF_DO + st * TILE; };
-  auto sPT = [&](int bf) { return sbase + OFF_PT + bf * PT_BYTES; };
+  const uint32_t sSTG = sbase + OFF_STG;
   auto sDS = [&](int bf) { return sbase + OFF_DS + bf * PT_BYTES; };
   float* lse_s = reinterpret_cast<float*>(smem + OFF_LSE);
   const uint32_t bar = sbase + OFF_BAR;
   const uint32_t kv_full = bar;
-  auto q_full = [&](int s) { return bar + 8u * (1 + s); };
-  auto q_empty = [&](int s) { return bar + 8u * (3 + s); };
+  auto q_full = [&](int s) { return bar + 8u * (16 + s); };
+  auto q_empty = [&](int s) { return bar + 8u * (19 + s); };
+  const uint32_t pt_free = bar + 8u * 1;
+  const uint32_t all_done = bar + 8u * 2;  // single phase: every MMA of this CTA retired
   const uint32_t s_full = bar + 8u * 5;
   const uint32_t pds_full = bar + 8u * 6;
-  auto dq_full = [&](int s) { return bar + 8u * (7 + s); };
-  auto dq_empty = [&](int s) { return bar + 8u * (9 + s); };
-  auto stg_free = [&](int s) { return bar + 8u * (11 + s); };
+  const uint32_t dq_full = bar + 8u * 7;
+  const uint32_t dq_empty = bar + 8u * 8;
   const uint32_t tmem_slot = bar + 8u * 13;
 
   const int warp = warp_idx_uniform();
@@ -122,17 +125,16 @@ attn_bwd64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   }
   if (warp == 1 && lane == 0) {
     mbar_init(kv_full, 1);
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < QS; ++s) {
       mbar_init(q_full(s), 1);
       mbar_init(q_empty(s), 1);
     }
+    mbar_init(pt_free, 1);
+    mbar_init(all_done, 1);
     mbar_init(s_full, 1);
     mbar_init(pds_full, 8);
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(dq_full(s), 1);
-      mbar_init(dq_empty(s), 4);
-      mbar_init(stg_free(s), 4);
-    }
+    mbar_init(dq_full, 1);
+    mbar_init(dq_empty, 4);
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, 512);
@@ -149,8 +151,8 @@ attn_bwd64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       tma_load_4d(sK, &tmK, kv_full, 0, hk, k0, b);
       tma_load_4d(sV, &tmV, kv_full, 0, hk, k0, b);
       for (int it = 0; it < n_it; ++it) {
-        const int st = it & 1;
-        const uint32_t ph = (it >> 1) & 1u;
+        const int st = it % QS;
+        const uint32_t ph = (it / QS) & 1u;
         const int h = hk * G + it / n_qt;
         const int q0 = (qt_first + it % n_qt) * BT;
         mbar_wait(q_empty(st), ph ^ 1u);
@@ -165,8 +167,8 @@ attn_bwd64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     constexpr uint32_t idesc_kv = make_idesc_bf16(128, D, false, true);    // K-major x MN-major
     constexpr uint32_t idesc_dq = make_idesc_bf16(128, D, true, true);     // MN-major x MN-major
     auto issue_s = [&](int it) {  // S^T = K Q^T, dP^T = V dO^T  (M = keys, N = queries, K = head dim)
-      const int st = it & 1;
-      mbar_wait(q_full(st), (it >> 1) & 1u);
+      const int st = it % QS;
+      mbar_wait(q_full(st), (it / QS) & 1u);
       tc_fence_after_sync();
       if (elect_one()) {
 #pragma unroll
@@ -184,36 +186,41 @@ attn_bwd64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     mbar_wait(kv_full, 0);
     if (n_it > 0) issue_s(0);
     for (int it = 0; it < n_it; ++it) {
-      const int st = it & 1, bf = it & 1;
+      const int st = it % QS, bf = it & 1;
       if (lane == 0) T64(8);
-      mbar_wait(pds_full, it & 1u);  // softmax(it) done: S/dP columns free, P^T/dS^T[bf] written
+      mbar_wait(pds_full, it & 1u);  // softmax(it) done: S/dP columns free, P^T (TMEM) and dS^T[bf] written
       if (lane == 0) T64(9);
       if (it + 1 < n_it) issue_s(it + 1);
       if (lane == 0) T64(10);
-      if (it > 1) mbar_wait(dq_empty(bf), ((it - 2) >> 1) & 1u);  // dQ(it-2) left this TMEM buffer
+      if (it > 0) mbar_wait(dq_empty, (it - 1) & 1u);  // dQ(it-1) copied out of TMEM by the drain warps
       tc_fence_after_sync();
       if (lane == 0) T64(11);
       if (elect_one()) {
-        // dV += P^T dO ; dK += dS^T Q  (M = keys, N = head dim, K = queries)
+        // dV += P^T dO  (M = keys, N = head dim, K = queries): A = P^T straight from TMEM, 8 packed columns
+        // per K step; then P^T may be overwritten by softmax(it+1)
 #pragma unroll
         for (int kk = 0; kk < BT / 16; ++kk)
-          umma_bf16_ss(tmem_base + TM_DV, make_smem_desc_sw128(sPT(bf) + (kk >> 2) * 16384 + (kk & 3) * 32, 0, 1024),
+          umma_bf16_ts(tmem_base + TM_DV, tmem_base + TM_PT + kk * 8,
                        make_smem_desc_sw128(sDO(st) + kk * 2048, 16384, 1024), idesc_kv, (it | kk) != 0);
+        umma_commit(pt_free);
+        // dK += dS^T Q
 #pragma unroll
         for (int kk = 0; kk < BT / 16; ++kk)
           umma_bf16_ss(tmem_base + TM_DK, make_smem_desc_sw128(sDS(bf) + (kk >> 2) * 16384 + (kk & 3) * 32, 0, 1024),
                        make_smem_desc_sw128(sQ(st) + kk * 2048, 16384, 1024), idesc_kv, (it | kk) != 0);
+        umma_commit(q_empty(st));  // Q / dO stage is last read by dV, dK
         // dQ = dS K  (M = queries, N = head dim, K = keys): dS^T tile read as an MN-major A operand
 #pragma unroll
         for (int kk = 0; kk < BT / 16; ++kk)
-          umma_bf16_ss(tmem_base + TM_DQ + 64 * bf, make_smem_desc_sw128(sDS(bf) + kk * 2048, 16384, 1024),
+          umma_bf16_ss(tmem_base + TM_DQ, make_smem_desc_sw128(sDS(bf) + kk * 2048, 16384, 1024),
                        make_smem_desc_sw128(sK + kk * 2048, 16384, 1024), idesc_dq, kk != 0);
-        umma_commit(q_empty(st));
-        umma_commit(dq_full(bf));
+        umma_commit(dq_full);
       }
       __syncwarp();
       if (lane == 0) T64(12);
     }
+    if (elect_one()) umma_commit(all_done);
+    __syncwarp();
   } else if (warp >= 10) {
     // ------------------------------------ dQ drain warpgroup --------------------------------------
     const int qd = warp & 3;
@@ -221,24 +228,22 @@ attn_bwd64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     const int dt = threadIdx.x - 320;  // 0..127
     const uint32_t t_lane = tmem_base + (uint32_t(qd * 32) << 16);
     for (int it = 0; it < n_it; ++it) {
-      const int bf = it & 1;
       const int h = hk * G + it / n_qt;
       const int q0 = (qt_first + it % n_qt) * BT;
-      mbar_wait(dq_full(bf), (it >> 1) & 1u);  // every MMA of `it` retired: dQ ready, P^T[bf] idle
+      mbar_wait(dq_full, it & 1u);  // every MMA of `it` retired
       tc_fence_after_sync();
       if (dt == 0) T64(13);
       uint32_t v[64];
-      tmem_ld_32x32b_x32(t_lane + TM_DQ + 64 * bf, v);
-      tmem_ld_32x32b_x32(t_lane + TM_DQ + 64 * bf + 32, v + 32);
+      tmem_ld_32x32b_x32(t_lane + TM_DQ, v);
+      tmem_ld_32x32b_x32(t_lane + TM_DQ + 32, v + 32);
       tmem_ld_wait();
       tc_fence_before_sync();
       __syncwarp();
-      if (lane == 0) mbar_arrive(dq_empty(bf));
+      if (lane == 0) mbar_arrive(dq_empty);
       // staging: [128 rows][16 chunks of 16 B], chunk ^= row & 15 (conflict-free both ways)
-      const uint32_t stg = sPT(bf);
 #pragma unroll
       for (int ch = 0; ch < 16; ++ch) {
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + row * 256 + ((ch ^ (row & 15)) << 4)),
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sSTG + row * 256 + ((ch ^ (row & 15)) << 4)),
                      "r"(v[ch * 4 + 0]), "r"(v[ch * 4 + 1]), "r"(v[ch * 4 + 2]), "r"(v[ch * 4 + 3])
                      : "memory");
       }
@@ -250,11 +255,9 @@ attn_bwd64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         const int r = c >> 4, ch = c & 15;
         asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
                      : "=f"(val[i].x), "=f"(val[i].y), "=f"(val[i].z), "=f"(val[i].w)
-                     : "r"(stg + r * 256 + ((ch ^ (r & 15)) << 4)));
+                     : "r"(sSTG + r * 256 + ((ch ^ (r & 15)) << 4)));
       }
-      // the tile is back in registers: hand P^T[bf] to the softmax of it + 2 before the slow part
-      __syncwarp();
-      if (lane == 0) mbar_arrive(stg_free(bf));
+      named_bar_sync(2, 128);  // everyone has its chunks in registers: the tile may be overwritten
       float* dst = p.dq_acc + (((long long)b * p.S + q0) * p.H + h) * D;
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
@@ -307,7 +310,6 @@ attn_bwd64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       if (it + 1 < n_it) lse_next = fetch_lse(it + 1);  // latency hides behind this iteration's softmax
       mbar_wait(s_full, it & 1u);
       tc_fence_after_sync();
-      if (it > 1) mbar_wait(stg_free(bf), ((it - 2) >> 1) & 1u);  // drain of it-2 no longer reads P^T[bf]
       if (threadIdx.x == 64) T64(1);
 #pragma unroll 1
       for (int c0 = cbase; c0 < cbase + 64; c0 += 32) {
@@ -315,7 +317,8 @@ attn_bwd64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         tmem_ld_32x32b_x32(t_lane + TM_S + c0, vs);
         tmem_ld_32x32b_x32(t_lane + TM_DP + c0, vd);
         tmem_ld_wait();
-        float pr[32], ds[32];
+        float ds[32];
+        uint32_t pk[16];
 #pragma unroll
         for (int g = 0; g < 8; ++g) {
           const float4 l4 = *reinterpret_cast<const float4*>(lse2 + c0 + g * 4);
@@ -327,16 +330,23 @@ attn_bwd64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
             const int qc = c0 + g * 4 + i;
             float e = ex2f(fmaf(__uint_as_float(vs[g * 4 + i]), sl2, -ls[i]));
             if ((diag && (q0 + qc < key)) || key >= p.S) e = 0.f;
-            pr[g * 4 + i] = e;
             ds[g * 4 + i] = e * (__uint_as_float(vd[g * 4 + i]) - dl[i]) * p.scale;
+            vs[g * 4 + i] = __float_as_uint(e);
           }
+          pk[g * 2] = pack_bf16x2(__uint_as_float(vs[g * 4]), __uint_as_float(vs[g * 4 + 1]));
+          pk[g * 2 + 1] = pack_bf16x2(__uint_as_float(vs[g * 4 + 2]), __uint_as_float(vs[g * 4 + 3]));
         }
+        // P^T: queries c0 .. c0+31 of this key row = packed columns c0/2 .. c0/2+15.  The previous tile's
+        // dV MMAs must have consumed the old contents first.
+        if (c0 == cbase && it > 0) {
+          mbar_wait(pt_free, (it - 1) & 1u);
+          tc_fence_after_sync();
+        }
+        tmem_st_32x32b_x16(t_lane + TM_PT + (c0 >> 1), pk);
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          st_tile_chunk(sPT(bf), row, (c0 >> 3) + g, pr + g * 8);
-          st_tile_chunk(sDS(bf), row, (c0 >> 3) + g, ds + g * 8);
-        }
+        for (int g = 0; g < 4; ++g) st_tile_chunk(sDS(bf), row, (c0 >> 3) + g, ds + g * 8);
       }
+      tmem_st_wait();
       tc_fence_before_sync();
       fence_proxy_async_smem();
       __syncwarp();
@@ -348,10 +358,9 @@ attn_bwd64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       named_bar_sync(1, 256);  // lse/delta slot of it+1 complete before anyone reads it
       if (threadIdx.x == 64) T64(5);
     }
-    if (n_it > 0) {
-      mbar_wait(dq_full((n_it - 1) & 1), ((n_it - 1) >> 1) & 1u);  // the last commit covers every MMA before it
-      tc_fence_after_sync();
-    }
+    // the softmax warps do not follow dq_full's phases, so a parity wait on it could alias: dedicated barrier
+    mbar_wait(all_done, 0);
+    tc_fence_after_sync();
 
     // dK / dV; column halves per warpgroup
 #pragma unroll 1

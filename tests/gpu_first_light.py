@@ -118,6 +118,35 @@ def sec_gemm_perf():
     OUT["gemm_perf"] = res
 
 
+@section("proj_perf")
+def sec_proj_perf():
+    """Library GEMM vs the hand-written GEMM on every projection shape of a C2 layer (T = 16384 tokens):
+    forward y = x W^T, dgrad dx = dy W, wgrad dW = dy^T x."""
+    T = 16384
+    res = []
+    for name, n_out, n_in in [("q/o", 1024, 1024), ("k/v", 512, 1024), ("gate/up", 2816, 1024), ("down", 1024, 2816)]:
+        x = torch.randn(T, n_in, device=DEV).to(torch.bfloat16)
+        w = (torch.randn(n_out, n_in, device=DEV) * 0.02).to(torch.bfloat16)
+        dy = torch.randn(T, n_out, device=DEV).to(torch.bfloat16)
+        y = torch.empty(T, n_out, device=DEV, dtype=torch.bfloat16)
+        dx = torch.empty(T, n_in, device=DEV, dtype=torch.bfloat16)
+        dw = torch.zeros(n_out, n_in, device=DEV, dtype=torch.bfloat16)
+        fl = 2.0 * T * n_out * n_in
+        row = {"proj": name}
+        for tag, lib_fn, my_fn in [
+            ("fwd", lambda: torch.nn.functional.linear(x, w), lambda: ops.gemm(x, w, out=y.unsqueeze(0))),
+            ("dgrad", lambda: torch.matmul(dy, w), lambda: ops.gemm(dy, w, b_mn=True, out=dx.unsqueeze(0))),
+            ("wgrad", lambda: dw.addmm_(dy.t(), x),
+             lambda: ops.gemm(dy, x, a_mn=True, b_mn=True, c=dw.unsqueeze(0), beta=1.0, out=dw.unsqueeze(0)))]:
+            ms_l, ms_m = time_cuda(lib_fn), time_cuda(my_fn)
+            row[tag] = {"lib_us": ms_l * 1e3, "mine_us": ms_m * 1e3, "lib_tf": fl / ms_l / 1e9, "mine_tf": fl / ms_m / 1e9}
+        print(f"proj_perf {name:8s} " + " | ".join(
+            f"{t}: lib {row[t]['lib_us']:.1f} us ({row[t]['lib_tf']:.0f} TF) mine {row[t]['mine_us']:.1f} us ({row[t]['mine_tf']:.0f} TF)"
+            for t in ("fwd", "dgrad", "wgrad")), flush=True)
+        res.append(row)
+    OUT["proj_perf"] = res
+
+
 NS_SHAPES_C2 = [(24, 1024, 1024), (24, 512, 1024), (24, 2816, 1024), (12, 1024, 2816), (1, 32003, 1024)]
 
 

@@ -72,7 +72,10 @@ def test_muon_steps_track_oracle(tmp_path):
 
 
 def test_adamw_fp32_steps_track_oracle(tmp_path):
-    tr = make_trainer(tmp_path, optimizer="adamw", mixed=False)
+    # lr 2e-3: at the tiny config's default 2e-2 this model diverges within three AdamW steps (attention scores
+    # reach +-170, loss goes up), and a per-step comparison of a chaotic trajectory measures rounding luck
+    # (tools/attn_debug.py replays it: every attention call stays within bf16 error of the dense reference)
+    tr = make_trainer(tmp_path, optimizer="adamw", mixed=False, hp__learning_rate=2e-3)
     for step in range(4):
         batch = tr.data_manager.generate_batch(step)
         before = masters(tr)
