@@ -406,16 +406,16 @@ attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __re
 }
 
 __global__ void __launch_bounds__(256)
-f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long nvec) {
+f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long nvec, float mul) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
        i += (long long)gridDim.x * blockDim.x) {
     const float4 a = *reinterpret_cast<const float4*>(src + i * 8);
     const float4 c = *reinterpret_cast<const float4*>(src + i * 8 + 4);
     uint4 o4;
-    o4.x = pack_bf16x2(a.x, a.y);
-    o4.y = pack_bf16x2(a.z, a.w);
-    o4.z = pack_bf16x2(c.x, c.y);
-    o4.w = pack_bf16x2(c.z, c.w);
+    o4.x = pack_bf16x2(a.x * mul, a.y * mul);
+    o4.y = pack_bf16x2(a.z * mul, a.w * mul);
+    o4.z = pack_bf16x2(c.x * mul, c.y * mul);
+    o4.w = pack_bf16x2(c.z * mul, c.w * mul);
     stg128(dst + i * 8, o4);
   }
 }
@@ -497,7 +497,8 @@ int attn_bwd(const void* q, const void* k, const void* v, const void* o, const v
     const char* e = getenv("B200_ATTN_BWD_V1");
     return e != nullptr && e[0] == '1';
   }();
-  if (D == 64 && !force_v1)  // software-pipelined head_dim-64 kernel (attention_bwd64.cu)
+  const bool pipelined64 = D == 64 && !force_v1;
+  if (pipelined64)  // software-pipelined head_dim-64 kernel (attention_bwd64.cu)
     rc = launch_attn_bwd64(tmQ, tmK, tmV, tmDO, lse, delta, dq_acc, dk, dv, B, S, H, Hk, scale, causal, stream);
   else
     rc = D == 64 ? launch_bwd<64>(tmQ, tmK, tmV, tmDO, a, stream) : launch_bwd<128>(tmQ, tmK, tmV, tmDO, a, stream);
@@ -506,7 +507,9 @@ int attn_bwd(const void* q, const void* k, const void* v, const void* o, const v
     const long long nvec = n / 8;
     long long blocks = (nvec + 255) / 256;
     if (blocks > (long long)num_sms() * 8) blocks = (long long)num_sms() * 8;
-    f32_to_bf16_kernel<<<(int)blocks, 256, 0, stream>>>(dq_acc, reinterpret_cast<__nv_bfloat16*>(dq), nvec);
+    // the pipelined kernel accumulates dS without the softmax scale (one multiply less per score): applied here
+    f32_to_bf16_kernel<<<(int)blocks, 256, 0, stream>>>(dq_acc, reinterpret_cast<__nv_bfloat16*>(dq), nvec,
+                                                        pipelined64 ? scale : 1.0f);
     B200_CHECK_LAUNCH();
   }
   return B200_OK;

@@ -305,6 +305,7 @@ attn_bwd64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       const float* lse2 = lse_s + (it & 1) * 256;
       const float* dlt = lse2 + 128;
       const bool diag = p.causal && q0 == k0;  // tiles are aligned: only the diagonal tile is cut
+      const bool need_mask = diag || (k0 + BT > p.S);  // CTA-uniform: off-diagonal full tiles skip all per-score tests
       if (threadIdx.x == 64) T64(0);
       float lse_next = 0.f;
       if (it + 1 < n_it) lse_next = fetch_lse(it + 1);  // latency hides behind this iteration's softmax
@@ -319,22 +320,42 @@ attn_bwd64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         tmem_ld_wait();
         float ds[32];
         uint32_t pk[16];
+        // dS here is P o (dP - delta) WITHOUT the softmax scale: dK and dQ are linear in dS, so the scale is
+        // applied once per output element (dK epilogue below, dQ conversion kernel) instead of once per score
+        if (!need_mask) {
 #pragma unroll
-        for (int g = 0; g < 8; ++g) {
-          const float4 l4 = *reinterpret_cast<const float4*>(lse2 + c0 + g * 4);
-          const float4 d4 = *reinterpret_cast<const float4*>(dlt + c0 + g * 4);
-          const float ls[4] = {l4.x, l4.y, l4.z, l4.w};
-          const float dl[4] = {d4.x, d4.y, d4.z, d4.w};
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int qc = c0 + g * 4 + i;
-            float e = ex2f(fmaf(__uint_as_float(vs[g * 4 + i]), sl2, -ls[i]));
-            if ((diag && (q0 + qc < key)) || key >= p.S) e = 0.f;
-            ds[g * 4 + i] = e * (__uint_as_float(vd[g * 4 + i]) - dl[i]) * p.scale;
-            vs[g * 4 + i] = __float_as_uint(e);
+          for (int g = 0; g < 8; ++g) {
+            const float4 l4 = *reinterpret_cast<const float4*>(lse2 + c0 + g * 4);
+            const float4 d4 = *reinterpret_cast<const float4*>(dlt + c0 + g * 4);
+            const float e0 = ex2f(fmaf(__uint_as_float(vs[g * 4 + 0]), sl2, -l4.x));
+            const float e1 = ex2f(fmaf(__uint_as_float(vs[g * 4 + 1]), sl2, -l4.y));
+            const float e2 = ex2f(fmaf(__uint_as_float(vs[g * 4 + 2]), sl2, -l4.z));
+            const float e3 = ex2f(fmaf(__uint_as_float(vs[g * 4 + 3]), sl2, -l4.w));
+            ds[g * 4 + 0] = e0 * (__uint_as_float(vd[g * 4 + 0]) - d4.x);
+            ds[g * 4 + 1] = e1 * (__uint_as_float(vd[g * 4 + 1]) - d4.y);
+            ds[g * 4 + 2] = e2 * (__uint_as_float(vd[g * 4 + 2]) - d4.z);
+            ds[g * 4 + 3] = e3 * (__uint_as_float(vd[g * 4 + 3]) - d4.w);
+            pk[g * 2] = pack_bf16x2(e0, e1);
+            pk[g * 2 + 1] = pack_bf16x2(e2, e3);
           }
-          pk[g * 2] = pack_bf16x2(__uint_as_float(vs[g * 4]), __uint_as_float(vs[g * 4 + 1]));
-          pk[g * 2 + 1] = pack_bf16x2(__uint_as_float(vs[g * 4 + 2]), __uint_as_float(vs[g * 4 + 3]));
+        } else {
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const float4 l4 = *reinterpret_cast<const float4*>(lse2 + c0 + g * 4);
+            const float4 d4 = *reinterpret_cast<const float4*>(dlt + c0 + g * 4);
+            const float ls[4] = {l4.x, l4.y, l4.z, l4.w};
+            const float dl[4] = {d4.x, d4.y, d4.z, d4.w};
+            float e[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int qc = c0 + g * 4 + i;
+              e[i] = ex2f(fmaf(__uint_as_float(vs[g * 4 + i]), sl2, -ls[i]));
+              if ((diag && (q0 + qc < key)) || key >= p.S) e[i] = 0.f;
+              ds[g * 4 + i] = e[i] * (__uint_as_float(vd[g * 4 + i]) - dl[i]);
+            }
+            pk[g * 2] = pack_bf16x2(e[0], e[1]);
+            pk[g * 2 + 1] = pack_bf16x2(e[2], e[3]);
+          }
         }
         // P^T: queries c0 .. c0+31 of this key row = packed columns c0/2 .. c0/2+15.  The previous tile's
         // dV MMAs must have consumed the old contents first.
@@ -369,6 +390,10 @@ attn_bwd64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       uint32_t v[32];
       tmem_ld_32x32b_x32(t_lane + (which == 0 ? TM_DV : TM_DK) + wg * 32, v);
       tmem_ld_wait();
+      if (which == 1) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * p.scale);
+      }
       if (key < p.S) {
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
