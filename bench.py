@@ -327,7 +327,8 @@ def main() -> None:
                 "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
                 "frac_of_burst": (ns_tf / peaks["bf16_tflops"]) if ns_tf else None,
                 "algorithmic_flops_per_step": ns_fl, "algorithmic_flops_all_ranks": ns_flops_per_step(),
-                "ns_sharded_over_ranks": sharded, "ms_per_step": ns_ms_step,
+                "ns_sharded_over_ranks": sharded, "ns_exchange": getattr(tr.optimizer, "exchange_mode", None),
+                "ms_per_step": ns_ms_step,
                 "share_of_step": ns_ms_step / ms_per_step if ms_per_step else None}
     kernels = {}
     afl = attn_flops_fwd_per_step()

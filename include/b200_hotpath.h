@@ -61,6 +61,16 @@ size_t b200_newton_schulz_workspace_bytes(int batch, int rows, int cols, int ste
 int b200_newton_schulz(const void* x_in, void* x_out, int batch, int rows, int cols, int steps,
                        float a, float b, float c, const float* inv_norm, const float* inv_norm_sq,
                        void* workspace, size_t workspace_bytes, void* stream);
+/* Same chain for the owner-computes data-parallel mode (SURVEY 8e "fused mode"; the reference's size-balanced
+ * ownership idea: modal/modal_cuda_utils.py:468-490).  peer_out[i] (HOST array of n_peers <= 7 device
+ * pointers) are peer-mapped addresses of the SAME x_out slot in the other ranks' buffers (NVLink peer
+ * memory, e.g. torch symmetric memory).  The last X' = aX + BX GEMM writes its tiles to x_out and to every
+ * peer from its epilogue -- GEMM and all-gather are one kernel; the caller only needs a cross-rank barrier
+ * before reading the gathered buffer. */
+int b200_newton_schulz_allgather(const void* x_in, void* x_out, int batch, int rows, int cols, int steps,
+                                 float a, float b, float c, const float* inv_norm,
+                                 const float* inv_norm_sq, void* workspace, size_t workspace_bytes,
+                                 const void* const* peer_out, int n_peers, void* stream);
 
 /* muon.py:101,105: buf = (1-mu)*g*gscale + mu*buf ; u = nesterov ? g*gscale + mu*buf : buf.
  * g: [batch,numel] bf16 (g_is_bf16=1) or f32; buf f32; u bf16; sumsq[b] = sum(u_b^2) (zeroed

@@ -25,6 +25,7 @@ SIGNATURES = {
                             _vp, _ll, _ll, _i, _f, _f, _vp, _vp, _i, _vp]),
     "b200_newton_schulz_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "b200_newton_schulz": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _f, _f, _vp, _vp, _vp, _sz, _vp]),
+    "b200_newton_schulz_allgather": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _f, _f, _vp, _vp, _vp, _sz, _vp, _i, _vp]),
     "b200_muon_momentum": (_i, [_vp, _i, _vp, _vp, _vp, _ll, _i, _f, _i, _f, _vp]),
     "b200_ns_scales": (_i, [_vp, _vp, _vp, _i, _f, _vp]),
     "b200_axpy_update": (_i, [_vp, _vp, _vp, _i, _ll, _f, _vp]),

@@ -12,7 +12,7 @@ int gemm_bf16(bool a_mn, bool b_mn, int M, int N, int K, int batch, const void* 
 size_t newton_schulz_workspace_bytes(int batch, int rows, int cols, int steps);
 int newton_schulz(const void* x_in, void* x_out, int batch, int rows, int cols, int steps, float a,
                   float b, float c, const float* inv_norm, const float* inv_norm_sq, void* ws,
-                  size_t ws_bytes, cudaStream_t stream);
+                  size_t ws_bytes, const void* const* peer_out, int n_peers, cudaStream_t stream);
 int muon_momentum(const void* g, int g_is_bf16, float* buf, void* u_bf16, float* sumsq,
                   long long numel, int batch, float mu, int nesterov, float gscale,
                   cudaStream_t stream);
@@ -98,7 +98,14 @@ int b200_newton_schulz(const void* x_in, void* x_out, int batch, int rows, int c
                        float a, float b, float c, const float* inv_norm, const float* inv_norm_sq,
                        void* workspace, size_t workspace_bytes, void* stream) {
   return b200::newton_schulz(x_in, x_out, batch, rows, cols, steps, a, b, c, inv_norm, inv_norm_sq,
-                             workspace, workspace_bytes, S_(stream));
+                             workspace, workspace_bytes, nullptr, 0, S_(stream));
+}
+int b200_newton_schulz_allgather(const void* x_in, void* x_out, int batch, int rows, int cols, int steps,
+                                 float a, float b, float c, const float* inv_norm, const float* inv_norm_sq,
+                                 void* workspace, size_t workspace_bytes, const void* const* peer_out,
+                                 int n_peers, void* stream) {
+  return b200::newton_schulz(x_in, x_out, batch, rows, cols, steps, a, b, c, inv_norm, inv_norm_sq,
+                             workspace, workspace_bytes, peer_out, n_peers, S_(stream));
 }
 int b200_muon_momentum(const void* g, int g_is_bf16, float* buf, void* u_bf16, float* sumsq,
                        long long numel, int batch, float mu, int nesterov, float gscale,

@@ -308,7 +308,8 @@ int gemm_bf16_2cta(bool a_mn, bool b_mn, int M, int N, int K, int batch, const v
                    long long strideA, const void* B, long long ldb, long long strideB, const void* C,
                    long long ldc, long long strideC, void* D, long long ldd, long long strideD, bool out_f32,
                    float alpha, float beta, const float* alpha_vec, const float* beta_vec, int bn,
-                   int symmetric, int k_splits, float* splitk_ws, cudaStream_t stream);
+                   int symmetric, int k_splits, float* splitk_ws, const void* const* peer_D, int n_peers,
+                   cudaStream_t stream);
 
 // Internal C++ entry (also used by the Newton-Schulz / Shampoo drivers).
 int gemm_bf16(bool a_mn, bool b_mn, int M, int N, int K, int batch, const void* A, long long lda,
@@ -348,7 +349,7 @@ int gemm_bf16(bool a_mn, bool b_mn, int M, int N, int K, int batch, const void* 
       if (force_bn == 128 || force_bn == 256) bn2 = force_bn;
       return gemm_bf16_2cta(a_mn, b_mn, M, N, K, batch, A, lda, strideA, B, ldb, strideB, C, ldc, strideC, D,
                             ldd, strideD, out_f32, alpha, beta, alpha_vec, beta_vec, bn2, symmetric, 1, nullptr,
-                            stream);
+                            nullptr, 0, stream);
     }
   }
 

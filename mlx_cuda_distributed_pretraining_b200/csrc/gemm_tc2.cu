@@ -37,7 +37,14 @@ struct Gemm2Args {
   int symmetric;  // D is symmetric (M == N, BN == 256): compute tiles with mi <= ni, mirror-write the rest
   int k_splits;   // > 1: every tile's K range is cut into k_splits work items, each storing its raw fp32
   float* ws;      //      partial into slab ws[split][batch][M][N]; splitk_finalize_kernel applies the epilogue
+  // GEMM -> all-gather in one kernel: besides D, the epilogue stores every output tile into the same offsets
+  // of `n_peers` peer-mapped copies of D (other GPUs' buffers over NVLink; torch symmetric memory).  Tiles
+  // leave through a per-warp smem transpose so that every store instruction writes 8 rows x 64 contiguous
+  // bytes (full sectors / NVLink flits) instead of 32 rows x 16 bytes.  bf16 output, non-symmetric only.
+  int n_peers;
+  void* peer_D[7];
 };
+constexpr int G2_MAX_PEERS = 7;
 
 // tile index -> (mi, ni).  Symmetric mode walks the upper triangle row by row.
 __device__ __forceinline__ void tile_coords(const Gemm2Args& p, int r, int& mi, int& ni) {
@@ -63,7 +70,8 @@ struct G2Cfg {
   static constexpr int STAGE_BYTES = G2_A_BYTES + B_BYTES;        // per CTA
   static constexpr int STAGES = (BN == 256) ? 6 : 8;
   static constexpr int TMEM_COLS = 2 * BN;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+  static constexpr int EPI_STAGE_BYTES = 8 * 2048;  // 8 epilogue warps x [32 rows x 64 B] transpose tiles
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + EPI_STAGE_BYTES;
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -134,6 +142,7 @@ gemm2_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+  const uint32_t epi_stage = bar_base + 256;  // after the barrier block
   auto smem_a = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES; };
   auto smem_b = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES + G2_A_BYTES; };
 
@@ -341,6 +350,55 @@ gemm2_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         uint32_t v[32];
         tmem_ld_32x32b_x32(t_row + c0, v);
         tmem_ld_wait();
+        if constexpr (VEC == 8) {
+          if (p.n_peers > 0) {
+            // ---- fused all-gather path: alpha/beta epilogue -> smem transpose -> coalesced local + peer stores
+            const uint32_t stg = epi_stage + (uint32_t)(warp - 4) * 2048u;
+#pragma unroll
+            for (int g = 0; g < 32; g += 8) {
+              float f[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) f[i] = alpha * __uint_as_float(v[g + i]);
+              if (crow && row_ok) {
+                const uint4 cv = cpre[(cc + g) / 8];
+                const float2 c01 = unpack_bf16x2(cv.x), c23 = unpack_bf16x2(cv.y), c45 = unpack_bf16x2(cv.z),
+                             c67 = unpack_bf16x2(cv.w);
+                f[0] = fmaf(beta, c01.x, f[0]);
+                f[1] = fmaf(beta, c01.y, f[1]);
+                f[2] = fmaf(beta, c23.x, f[2]);
+                f[3] = fmaf(beta, c23.y, f[3]);
+                f[4] = fmaf(beta, c45.x, f[4]);
+                f[5] = fmaf(beta, c45.y, f[5]);
+                f[6] = fmaf(beta, c67.x, f[6]);
+                f[7] = fmaf(beta, c67.y, f[7]);
+              }
+              const int piece = g >> 3;
+              const uint32_t addr = stg + lane * 64 + (((piece ^ ((lane >> 1) & 3))) << 4);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pack_bf16x2(f[0], f[1])),
+                           "r"(pack_bf16x2(f[2], f[3])), "r"(pack_bf16x2(f[4], f[5])), "r"(pack_bf16x2(f[6], f[7]))
+                           : "memory");
+            }
+            __syncwarp();
+            const int piece = lane & 3;
+            const int gn = n0 + c0 + piece * 8;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int r = i * 8 + (lane >> 2);  // row within this warp's 32
+              uint4 o;
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                           : "=r"(o.x), "=r"(o.y), "=r"(o.z), "=r"(o.w)
+                           : "r"(stg + r * 64 + ((piece ^ ((r >> 1) & 3)) << 4)));
+              const int grow = m0 + q * 32 + r;
+              if (grow < p.M && gn < p.N) {
+                const long long off = (long long)b * p.strideD + (long long)grow * p.ldd + gn;
+                stg128(reinterpret_cast<OutT*>(p.D) + off, o);
+                for (int pr = 0; pr < p.n_peers; ++pr) stg128(reinterpret_cast<OutT*>(p.peer_D[pr]) + off, o);
+              }
+            }
+            __syncwarp();
+            continue;
+          }
+        }
         if (row_ok) {
 #pragma unroll
           for (int g = 0; g < 32; g += VEC) {
@@ -497,8 +555,13 @@ int gemm_bf16_2cta(bool a_mn, bool b_mn, int M, int N, int K, int batch, const v
                    long long strideA, const void* B, long long ldb, long long strideB, const void* C,
                    long long ldc, long long strideC, void* D, long long ldd, long long strideD, bool out_f32,
                    float alpha, float beta, const float* alpha_vec, const float* beta_vec, int bn,
-                   int symmetric, int k_splits, float* splitk_ws, cudaStream_t stream) {
+                   int symmetric, int k_splits, float* splitk_ws, const void* const* peer_D, int n_peers,
+                   cudaStream_t stream) {
   if (symmetric && (M != N || bn != 256 || out_f32)) symmetric = 0;  // square bf16 256-tiles only
+  B200_CHECK_ARG(n_peers >= 0 && n_peers <= G2_MAX_PEERS, "gemm: n_peers=%d out of range (0..%d)", n_peers,
+                 G2_MAX_PEERS);
+  B200_CHECK_ARG(n_peers == 0 || (!out_f32 && !symmetric && k_splits <= 1),
+                 "gemm: peer stores need a bf16, non-symmetric, non-split-K output");
   // split-K needs a plain alpha-only bf16 epilogue and 16-byte partial rows
   if (k_splits > 1 && (!splitk_ws || out_f32 || beta != 0.0f || (N & 7) != 0)) k_splits = 1;
   if (k_splits < 1) k_splits = 1;
@@ -537,6 +600,8 @@ int gemm_bf16_2cta(bool a_mn, bool b_mn, int M, int N, int K, int batch, const v
   a.symmetric = symmetric;
   a.k_splits = k_splits;
   a.ws = splitk_ws;
+  a.n_peers = n_peers;
+  for (int i = 0; i < G2_MAX_PEERS; ++i) a.peer_D[i] = i < n_peers ? const_cast<void*>(peer_D[i]) : nullptr;
   int rc;
   if (!a_mn && !b_mn) rc = dispatch2<false, false>(out_f32, bn, tmA, tmB, a, stream);
   else if (!a_mn && b_mn) rc = dispatch2<false, true>(out_f32, bn, tmA, tmB, a, stream);

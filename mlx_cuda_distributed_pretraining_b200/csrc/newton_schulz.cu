@@ -22,7 +22,8 @@ int gemm_bf16_2cta(bool a_mn, bool b_mn, int M, int N, int K, int batch, const v
                    long long strideA, const void* B, long long ldb, long long strideB, const void* C,
                    long long ldc, long long strideC, void* D, long long ldd, long long strideD, bool out_f32,
                    float alpha, float beta, const float* alpha_vec, const float* beta_vec, int bn,
-                   int symmetric, int k_splits, float* splitk_ws, cudaStream_t stream);
+                   int symmetric, int k_splits, float* splitk_ws, const void* const* peer_D, int n_peers,
+                   cudaStream_t stream);
 
 static inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
 
@@ -53,9 +54,14 @@ size_t newton_schulz_workspace_bytes(int batch, int rows, int cols, int steps) {
   return bytes;
 }
 
+// peer_out / n_peers: peer-mapped copies of x_out on other GPUs (owner-computes Newton-Schulz under data
+// parallelism).  The LAST iteration's X' = aX + BX GEMM then stores its tiles to x_out and to every peer
+// from its epilogue (GEMM -> all-gather in one kernel); with n_peers == 0 this is the plain chain.
 int newton_schulz(const void* x_in, void* x_out, int batch, int rows, int cols, int steps, float a,
                   float b, float c, const float* inv_norm, const float* inv_norm_sq, void* ws,
-                  size_t ws_bytes, cudaStream_t stream) {
+                  size_t ws_bytes, const void* const* peer_out, int n_peers, cudaStream_t stream) {
+  B200_CHECK_ARG(n_peers >= 0 && n_peers <= 7 && (n_peers == 0 || peer_out != nullptr),
+                 "newton_schulz: bad peer list (n_peers=%d)", n_peers);
   B200_CHECK_ARG(batch > 0 && rows > 0 && cols > 0 && steps > 0,
                  "newton_schulz: bad shape batch=%d rows=%d cols=%d steps=%d", batch, rows, cols,
                  steps);
@@ -89,7 +95,7 @@ int newton_schulz(const void* x_in, void* x_out, int batch, int rows, int cols, 
     if (splits > 1)
       rc_ = gemm_bf16_2cta(tall, tall, m, m, tall ? rows : cols, batch, cur, cols, rc, cur, cols, rc, nullptr,
                            0, 0, Abuf, m, mm, false, 1.0f, 0.0f, s2, nullptr, 256, 1, splits, splitk_ws,
-                           stream);
+                           nullptr, 0, stream);
     else if (!tall)
       rc_ = gemm_bf16(false, false, m, m, cols, batch, cur, cols, rc, cur, cols, rc, nullptr, 0, 0,
                       Abuf, m, mm, false, 1.0f, 0.0f, s2, nullptr, kSym, stream);
@@ -101,13 +107,33 @@ int newton_schulz(const void* x_in, void* x_out, int batch, int rows, int cols, 
     rc_ = gemm_bf16(false, false, m, m, m, batch, Abuf, m, mm, Abuf, m, mm, Abuf, m, mm, Bbuf, m,
                     mm, false, c, b, nullptr, nullptr, kSym, stream);
     if (rc_) return rc_;
-    // G3
-    if (!tall)
-      rc_ = gemm_bf16(false, true, m, cols, m, batch, Bbuf, m, mm, cur, cols, rc, cur, cols, rc,
-                      nxt, cols, rc, false, 1.0f, a, s1, s1, 0, stream);
-    else
-      rc_ = gemm_bf16(false, false, rows, m, m, batch, cur, cols, rc, Bbuf, m, mm, cur, cols, rc,
-                      nxt, cols, rc, false, 1.0f, a, s1, s1, 0, stream);
+    // G3 (the last one carries the peer stores)
+    const bool last = it == steps - 1;
+    const int g3_m = tall ? rows : m, g3_n = tall ? m : cols;
+    if (last && n_peers > 0 && g3_m > 128) {
+      // CTA-pair kernel directly: tile-N choice as in gemm_bf16
+      const long long t256 = (long long)((g3_m + 255) / 256) * ((g3_n + 255) / 256) * batch;
+      const int bn2 = (g3_n <= 128 || t256 < (num_sms() / 2) * 3 / 4) ? 128 : 256;
+      if (!tall)
+        rc_ = gemm_bf16_2cta(false, true, m, cols, m, batch, Bbuf, m, mm, cur, cols, rc, cur, cols, rc, nxt, cols,
+                             rc, false, 1.0f, a, s1, s1, bn2, 0, 1, nullptr, peer_out, n_peers, stream);
+      else
+        rc_ = gemm_bf16_2cta(false, false, rows, m, m, batch, cur, cols, rc, Bbuf, m, mm, cur, cols, rc, nxt, cols,
+                             rc, false, 1.0f, a, s1, s1, bn2, 0, 1, nullptr, peer_out, n_peers, stream);
+    } else {
+      if (!tall)
+        rc_ = gemm_bf16(false, true, m, cols, m, batch, Bbuf, m, mm, cur, cols, rc, cur, cols, rc,
+                        nxt, cols, rc, false, 1.0f, a, s1, s1, 0, stream);
+      else
+        rc_ = gemm_bf16(false, false, rows, m, m, batch, cur, cols, rc, Bbuf, m, mm, cur, cols, rc,
+                        nxt, cols, rc, false, 1.0f, a, s1, s1, 0, stream);
+      if (rc_ == 0 && last && n_peers > 0) {
+        // small matrices run on the single-CTA kernel, which has no peer epilogue: copy the result out
+        for (int pi = 0; pi < n_peers; ++pi)
+          B200_CHECK_CUDA(cudaMemcpyAsync(const_cast<void*>(peer_out[pi]), nxt, (size_t)batch * rc * 2,
+                                          cudaMemcpyDeviceToDevice, stream));
+      }
+    }
     if (rc_) return rc_;
     cur = nxt;
   }

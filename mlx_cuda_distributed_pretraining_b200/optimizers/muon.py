@@ -16,12 +16,18 @@ Data parallel (`shard_ns=True`, set by the trainer when world > 1): gradients ar
 all-reduced, so every rank holds the same momentum; each rank then orthogonalises only its slice
 of every shape group (owner computes) and the results are exchanged with one in-place all-gather
 per group (a broadcast for groups with fewer matrices than ranks), issued asynchronously so the
-gather of group g overlaps the Newton-Schulz GEMMs of group g+1.  Communication volume equals
+gather of group g overlaps the Newton-Schulz GEMMs of group g+1.  When the ranks can map each
+other's memory (torch symmetric memory over NVLink; `B200_NS_P2P=0` disables) the gather is not a
+separate collective at all: the gather buffers are peer-mapped and the LAST GEMM of each chain
+stores its output tiles into every rank's buffer from its epilogue
+(`b200_newton_schulz_allgather`), followed by one cross-rank barrier before the apply kernels.  Communication volume equals
 the gradient all-reduce's all-gather half; Newton-Schulz work per rank drops by ~1/world
 (SURVEY 8e "fused mode", modal/modal_cuda_utils.py:468-490 for the size-balanced ownership idea).
 """
 from __future__ import annotations
 
+import ctypes
+import os
 from typing import Callable, Dict, Optional, Tuple, Union
 
 import torch
@@ -76,6 +82,7 @@ class Muon:
         self._u = torch.empty(max(max_numel, 8), dtype=torch.bfloat16, device=dev)
         self._x = torch.empty(max(max_numel, 8), dtype=torch.bfloat16, device=dev)
         self._xg = None  # per-group gather buffers of the sharded mode (allocated on first use)
+        self._xg_handles = None  # symmetric-memory handles when the buffers are peer-mapped
         self._ws = torch.empty(max(ws_bytes, 256), dtype=torch.uint8, device=dev)
         self._ss = torch.empty(max_batch, dtype=torch.float32, device=dev)
         self._inv = torch.empty(max_batch, dtype=torch.float32, device=dev)
@@ -105,9 +112,8 @@ class Muon:
         world = dp.world_size() if self.shard_ns else 1
         rank = dp.env_rank_world()[0] if world > 1 else 0
         if world > 1 and self._xg is None:
-            # one padded buffer per group: world * ceil(batch/world) matrices, so gathers can stay in flight
-            self._xg = [torch.empty(max(g.batch, world * dp.chunk_ranges(g.batch, world)[0]) * g.rows * g.cols,
-                                    dtype=torch.bfloat16, device=store.device) for g in store.mat_groups]
+            self._alloc_gather_buffers(store, world)
+        p2p = world > 1 and self._xg_handles is not None
         pending = []
         for gi, g in enumerate(store.mat_groups):
             n = g.numel
@@ -128,6 +134,15 @@ class Muon:
             for lo, hi in mine:
                 if hi <= lo:
                     continue
+                if p2p:   # GEMM -> all-gather in one kernel: the last GEMM stores into every rank's buffer
+                    ptrs = [int(bp) + 2 * lo * rc for r, bp in enumerate(self._xg_handles[gi].buffer_ptrs) if r != rank]
+                    peers = (ctypes.c_void_p * len(ptrs))(*ptrs)
+                    ops.check(lib.b200_newton_schulz_allgather(
+                        u.data_ptr() + 2 * lo * rc, x.data_ptr() + 2 * lo * rc, hi - lo, g.rows, g.cols,
+                        self.ns_steps, a, b, c, self._inv.data_ptr() + 4 * lo, self._inv2.data_ptr() + 4 * lo,
+                        self._ws.data_ptr(), self._ws.numel(), peers, len(ptrs), stream),
+                        "b200_newton_schulz_allgather")
+                    continue
                 ops.check(lib.b200_newton_schulz(u.data_ptr() + 2 * lo * rc, x.data_ptr() + 2 * lo * rc, hi - lo,
                                                  g.rows, g.cols, self.ns_steps, a, b, c,
                                                  self._inv.data_ptr() + 4 * lo, self._inv2.data_ptr() + 4 * lo,
@@ -135,7 +150,7 @@ class Muon:
                           "b200_newton_schulz")
             ops._t1(tok)
             works = []
-            if world > 1:
+            if world > 1 and not p2p:
                 if g.batch >= world:
                     works.append(dp.all_gather_chunks_(x, chunk * rc, async_op=True))
                 else:
@@ -145,6 +160,9 @@ class Muon:
             if world == 1:
                 self._apply(store, g, x, lr, lib, stream)   # the single x buffer is reused by the next group
                 pending.pop()
+        if p2p:
+            # every rank's peer stores are stream-ordered before its barrier arrival
+            self._xg_handles[0].barrier()
         for g, x, works in pending:
             for w in works:
                 if w is not None:
@@ -159,6 +177,31 @@ class Muon:
                 ops.sgd_momentum(store.master[lo:hi], p16, gsrc[lo:hi], self._buf[lo:hi], self.momentum,
                                  self.nesterov, lr, self.grad_scale)
         self.count += 1
+
+    def _alloc_gather_buffers(self, store, world: int) -> None:
+        """One padded buffer per shape group: world * ceil(batch/world) matrices, so exchanges can stay in
+        flight.  Peer-mapped (symmetric memory) when possible, plain device memory + NCCL otherwise."""
+        sizes = [max(g.batch, world * dp.chunk_ranges(g.batch, world)[0]) * g.rows * g.cols for g in store.mat_groups]
+        if os.environ.get("B200_NS_P2P", "1") != "0" and world <= 8:
+            try:
+                import torch.distributed as dist
+                import torch.distributed._symmetric_memory as symm
+                bufs = [symm.empty(n, dtype=torch.bfloat16, device=store.device) for n in sizes]
+                self._xg_handles = [symm.rendezvous(t, group=dist.group.WORLD) for t in bufs]
+                self._xg = bufs
+                return
+            except Exception as e:  # no peer mapping on this machine: NCCL exchange instead
+                self._xg_handles = None
+                if os.environ.get("B200_NS_P2P") == "1":
+                    raise
+                print(f"[muon] symmetric memory unavailable ({type(e).__name__}: {e}); using NCCL all-gather")
+        self._xg = [torch.empty(n, dtype=torch.bfloat16, device=store.device) for n in sizes]
+
+    @property
+    def exchange_mode(self) -> str:
+        if not self.shard_ns or self._xg is None:
+            return "replicated" if not self.shard_ns else "sharded (not started)"
+        return "fused GEMM+all-gather over peer memory" if self._xg_handles is not None else "NCCL all-gather"
 
     @staticmethod
     def owned_ranges(batch: int, world: int, rank: int):

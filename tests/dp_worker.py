@@ -24,6 +24,7 @@ def main():
     torch.cuda.synchronize()
     assert getattr(tr.optimizer, "shard_ns", False), "owner-computes Newton-Schulz should be on under DP"
     torch.save({n: t.detach().cpu() for n, t in tr.store.named_master().items()}, out / f"dp_rank{tr.rank}.pt")
+    (out / f"exchange_rank{tr.rank}.txt").write_text(tr.optimizer.exchange_mode)
     dp.barrier()
     dp.destroy()
 
