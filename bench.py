@@ -315,9 +315,9 @@ def main() -> None:
     # flops of the matrices THIS rank orthogonalised (all of them unless the owner-computes mode is on)
     sharded = bool(getattr(tr.optimizer, "shard_ns", False)) and world > 1
     ns_fl = 0.0
-    for g in tr.store.mat_groups:
+    for gi, g in enumerate(tr.store.mat_groups):
         m, n = min(g.rows, g.cols), max(g.rows, g.cols)
-        owned = sum(hi - lo for lo, hi in tr.optimizer.owned_ranges(g.batch, world if sharded else 1, rank))
+        owned = sum(hi - lo for lo, hi in tr.optimizer.owned_ranges_of(gi, world if sharded else 1, rank))
         ns_fl += owned * 5.0 * (4.0 * m * m * n + 2.0 * m ** 3)
     ns_tf = ns_fl / (ns_ms_step * 1e-3) / 1e12 if ns_ms_step > 0 else None
     peak_tf = peaks["bf16_tflops_sustained"]

@@ -100,6 +100,31 @@ def small_group_owner(index: int, world: int) -> int:
     return world - 1 - (index % world)
 
 
+def balanced_ranges(groups: List[Tuple[int, float]], world: int) -> List[List[Tuple[int, int, int]]]:
+    """Cost-balanced contiguous ownership over the concatenation of all shape groups.
+    groups[g] = (batch_g, cost_per_matrix_g).  Matrix i (global order) goes to rank
+    floor(midpoint_i / (total / world)), so every rank owns ONE contiguous run that crosses few group
+    boundaries: few, large batched launches per rank instead of a sliver of every group (the equal-chunk
+    split an NCCL all-gather needs).  Returns per rank a list of (group, lo, hi).  Needs an exchange that
+    accepts arbitrary ownership (the peer-memory epilogue stores)."""
+    total = sum(b * c for b, c in groups)
+    target = total / world if total > 0 else 1.0
+    out: List[List[Tuple[int, int, int]]] = [[] for _ in range(world)]
+    prefix = 0.0
+    for g, (batch, cost) in enumerate(groups):
+        run_rank, run_lo = None, 0
+        for i in range(batch):
+            r = min(world - 1, int((prefix + 0.5 * cost) / target))
+            prefix += cost
+            if r != run_rank:
+                if run_rank is not None:
+                    out[run_rank].append((g, run_lo, i))
+                run_rank, run_lo = r, i
+        if run_rank is not None:
+            out[run_rank].append((g, run_lo, batch))
+    return out
+
+
 def all_gather_chunks_(full: torch.Tensor, chunk_elems: int, async_op: bool = False):
     """In-place all-gather: rank r contributes full[r*chunk : (r+1)*chunk], every rank ends with all
     world*chunk elements.  Returns the work handle when async_op (None on a single process)."""

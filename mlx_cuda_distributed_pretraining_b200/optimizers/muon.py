@@ -83,6 +83,7 @@ class Muon:
         self._x = torch.empty(max(max_numel, 8), dtype=torch.bfloat16, device=dev)
         self._xg = None  # per-group gather buffers of the sharded mode (allocated on first use)
         self._xg_handles = None  # symmetric-memory handles when the buffers are peer-mapped
+        self._use_multicast = False
         self._ws = torch.empty(max(ws_bytes, 256), dtype=torch.uint8, device=dev)
         self._ss = torch.empty(max_batch, dtype=torch.float32, device=dev)
         self._inv = torch.empty(max_batch, dtype=torch.float32, device=dev)
@@ -128,14 +129,20 @@ class Muon:
                                              float(self.grad_scale), stream), "b200_muon_momentum")
             ops.check(lib.b200_ns_scales(self._ss.data_ptr(), self._inv.data_ptr(), self._inv2.data_ptr(),
                                          g.batch, ops.NS_EPS, stream), "b200_ns_scales")
-            mine = self.owned_ranges(g.batch, world, rank)   # matrices this rank orthogonalises
+            mine = self.owned_ranges_of(gi, world, rank)   # matrices this rank orthogonalises
             chunk = dp.chunk_ranges(g.batch, world)[0]
             tok = ops._t0("newton_schulz")
             for lo, hi in mine:
                 if hi <= lo:
                     continue
                 if p2p:   # GEMM -> all-gather in one kernel: the last GEMM stores into every rank's buffer
-                    ptrs = [int(bp) + 2 * lo * rc for r, bp in enumerate(self._xg_handles[gi].buffer_ptrs) if r != rank]
+                    hdl = self._xg_handles[gi]
+                    if self._use_multicast:
+                        # one store to the NVSwitch multicast address reaches every rank's replica: per-rank
+                        # NVLink egress is its own share, not (world - 1) copies of it
+                        ptrs = [int(hdl.multicast_ptr) + 2 * lo * rc]
+                    else:
+                        ptrs = [int(bp) + 2 * lo * rc for r, bp in enumerate(hdl.buffer_ptrs) if r != rank]
                     peers = (ctypes.c_void_p * len(ptrs))(*ptrs)
                     ops.check(lib.b200_newton_schulz_allgather(
                         u.data_ptr() + 2 * lo * rc, x.data_ptr() + 2 * lo * rc, hi - lo, g.rows, g.cols,
@@ -189,6 +196,11 @@ class Muon:
                 bufs = [symm.empty(n, dtype=torch.bfloat16, device=store.device) for n in sizes]
                 self._xg_handles = [symm.rendezvous(t, group=dist.group.WORLD) for t in bufs]
                 self._xg = bufs
+                # multicast pays off once a unicast exchange would send several copies (measured at 2 ranks:
+                # one unicast copy 27.5 ms/step vs multicast 28.0); B200_NS_MULTICAST=1/0 forces it on/off
+                mc_env = os.environ.get("B200_NS_MULTICAST", "auto")
+                mc_ok = all(int(getattr(h, "multicast_ptr", 0) or 0) != 0 for h in self._xg_handles)
+                self._use_multicast = mc_ok and (mc_env == "1" or (mc_env == "auto" and world >= 4))
                 return
             except Exception as e:  # no peer mapping on this machine: NCCL exchange instead
                 self._xg_handles = None
@@ -201,7 +213,26 @@ class Muon:
     def exchange_mode(self) -> str:
         if not self.shard_ns or self._xg is None:
             return "replicated" if not self.shard_ns else "sharded (not started)"
-        return "fused GEMM+all-gather over peer memory" if self._xg_handles is not None else "NCCL all-gather"
+        if self._xg_handles is None:
+            return "NCCL all-gather"
+        return ("fused GEMM+all-gather, NVSwitch multicast stores" if self._use_multicast
+                else "fused GEMM+all-gather, unicast peer stores")
+
+    def owned_ranges_of(self, gi: int, world: int, rank: int):
+        """[lo, hi) ranges of shape group `gi` this rank orthogonalises.  With the peer-memory exchange any
+        ownership works, so the split is flop-balanced over ALL matrices (dp.balanced_ranges: at 8 ranks a
+        rank runs one or two long batched chains instead of 3-matrix slivers of every group); the NCCL
+        exchange needs the equal-chunk split of `owned_ranges`."""
+        g = self._store.mat_groups[gi]
+        if world <= 1 or self._xg_handles is None:
+            return self.owned_ranges(g.batch, world, rank)
+        if getattr(self, "_plan_world", None) != world:
+            def cost(r, c):
+                m, n = min(r, c), max(r, c)
+                return 4.0 * m * m * n + 2.0 * m ** 3
+            self._plan = dp.balanced_ranges([(q.batch, cost(q.rows, q.cols)) for q in self._store.mat_groups], world)
+            self._plan_world = world
+        return [(lo, hi) for (gg, lo, hi) in self._plan[rank] if gg == gi]
 
     @staticmethod
     def owned_ranges(batch: int, world: int, rank: int):

@@ -85,3 +85,21 @@ def test_owner_partition_covers_every_matrix_once():
                 owned = sorted(i for r in range(world) for i in range(batch) if dp.small_group_owner(i, world) == r)
                 assert dp.small_group_owner(0, world) == world - 1
             assert owned == list(range(batch))
+    # flop-balanced contiguous plan (peer-memory exchange): C2's five shape groups over 8 ranks
+    def cost(r, c):
+        m, n = min(r, c), max(r, c)
+        return 4.0 * m * m * n + 2.0 * m ** 3
+    groups = [(1, cost(32003, 1024)), (24, cost(1024, 1024)), (24, cost(512, 1024)), (24, cost(2816, 1024)),
+              (12, cost(1024, 2816))]
+    for world in (2, 4, 8):
+        plan = dp.balanced_ranges(groups, world)
+        seen = {g: [] for g in range(len(groups))}
+        loads = []
+        for r in range(world):
+            loads.append(sum((hi - lo) * groups[g][1] for g, lo, hi in plan[r]))
+            for g, lo, hi in plan[r]:
+                seen[g] += list(range(lo, hi))
+        assert all(sorted(seen[g]) == list(range(groups[g][0])) for g in seen)       # every matrix exactly once
+        biggest = max(c for _, c in groups)
+        assert max(loads) <= sum(loads) / world + biggest                            # balanced up to one matrix
+        assert max(len(p) for p in plan) <= 4                                        # few chains per rank
