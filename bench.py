@@ -310,6 +310,13 @@ def main() -> None:
         return
 
     peaks = load_peaks()
+    traffic, traffic_src = None, None
+    for tf_path in sorted(ROOT.glob("profiles/*_gemm_traffic.json")):   # written by tools/summarize_profiles.py
+        try:
+            traffic = float(json.loads(tf_path.read_text())["mean_dram_bytes_per_launch"])
+            traffic_src = f"{tf_path.relative_to(ROOT)} (ncu --set full, mean DRAM read+write bytes per launch)"
+        except Exception:
+            pass
     ns_ms, ns_calls = kt.get("newton_schulz", (0.0, 0))
     ns_ms_step = ns_ms / K if K else 0.0
     # flops of the matrices THIS rank orthogonalised (all of them unless the owner-computes mode is on)
@@ -323,7 +330,7 @@ def main() -> None:
     peak_tf = peaks["bf16_tflops_sustained"]
     roofline = {"kernel": "gemm2_bf16_tc_kernel (Newton-Schulz chain, 15 batched tcgen05 cta_group::2 GEMMs x 5 shape groups)",
                 "bound": "tensor", "achieved": ns_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": (ns_tf / peak_tf) if ns_tf else None, "traffic": None,
+                "frac": (ns_tf / peak_tf) if ns_tf else None, "traffic": traffic, "traffic_source": traffic_src,
                 "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
                 "frac_of_burst": (ns_tf / peaks["bf16_tflops"]) if ns_tf else None,
                 "algorithmic_flops_per_step": ns_fl, "algorithmic_flops_all_ranks": ns_flops_per_step(),

@@ -66,6 +66,19 @@ def full_captures():
             name = re.sub(r"\(.*", "", r[hdr.index("Kernel Name")]).replace("void ", "").replace("b200::<unnamed>::", "")
             md.append(f"| `{name}` | " + " | ".join(f"{r[hdr.index(k)]} {units[hdr.index(k)]}" for k in keys) + " |")
         md.append("")
+        if rep.stem.endswith("prof_gemm") and "dram__bytes_read.sum" in hdr:
+            # DRAM traffic per launch of the dominant kernel -> bench.py's roofline.traffic
+            def to_bytes(v, u):
+                return float(v.replace(",", "")) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
+            per = [to_bytes(r[hdr.index("dram__bytes_read.sum")], units[hdr.index("dram__bytes_read.sum")]) +
+                   to_bytes(r[hdr.index("dram__bytes_write.sum")], units[hdr.index("dram__bytes_write.sum")])
+                   for r in rows[2:]]
+            import json
+            (OUT / f"{R}_gemm_traffic.json").write_text(json.dumps({
+                "kernel": "gemm2_bf16_tc_kernel", "launches": len(per), "dram_bytes_per_launch": per,
+                "mean_dram_bytes_per_launch": sum(per) / len(per),
+                "note": "ncu --set full, launches 60..63 of tests/gpu_first_light.py ns_perf (batch-24 1024x1024 "
+                        "group: G1 reads X = 50.3 MB algorithmic; G3 reads B + X and writes X' = 151 MB)"}, indent=1))
     (OUT / f"{R}_ncu_full.md").write_text("\n".join(md) + "\n")
     print("wrote", OUT / f"{R}_ncu_full.md")
 
