@@ -370,6 +370,78 @@ def _precision_dtype(system: SystemConfig) -> torch.dtype:
     return torch.bfloat16
 
 
+class BatchPrefetcher:
+    """Background producer of token batches (the reference builds every batch on the
+    training thread, core/training.py:519-543,1651).  A daemon thread runs `make_batch(step)` for the
+    coming steps into a rotating pool of PINNED host buffers; `get(step)` hands the training loop the
+    buffer for exactly that step, so tokenisation / padding / the pinned staging copy overlap the GPU
+    step and the loop's own work is one asynchronous H2D copy.  A buffer is only rewritten after the
+    copy that read it has completed (`release(step, event)`)."""
+
+    def __init__(self, make_batch: Callable[[int], torch.Tensor], start: int, stop: int, depth: int = 2,
+                 pin: bool = True):
+        import queue
+        import threading
+        self._make, self._stop_step, self._depth = make_batch, stop, max(1, depth)
+        self._pin = pin and torch.cuda.is_available()
+        self._q: "queue.Queue" = queue.Queue(maxsize=self._depth)
+        self._pool: List[Optional[torch.Tensor]] = [None] * (self._depth + 2)
+        self._events: List[Any] = [None] * (self._depth + 2)
+        self._halt = threading.Event()
+        self._next = start
+        self._thread = threading.Thread(target=self._run, args=(start,), daemon=True, name="batch-prefetch")
+        self._thread.start()
+
+    def _run(self, start: int) -> None:
+        try:
+            for step in range(start, self._stop_step):
+                if self._halt.is_set():
+                    return
+                batch = self._make(step)
+                slot = (step - start) % len(self._pool)
+                ev = self._events[slot]
+                if ev is not None:
+                    ev.synchronize()          # the H2D copy that last read this buffer has finished
+                    self._events[slot] = None
+                buf = self._pool[slot]
+                if buf is None or buf.shape != batch.shape or buf.dtype != batch.dtype:
+                    buf = torch.empty(batch.shape, dtype=batch.dtype, pin_memory=self._pin)
+                    self._pool[slot] = buf
+                buf.copy_(batch)
+                while not self._halt.is_set():
+                    try:
+                        self._q.put((step, slot, buf), timeout=0.1)
+                        break
+                    except Exception:
+                        continue
+        except BaseException as e:  # surfaced to the training thread by get()
+            self._q.put((None, None, e))
+
+    def get(self, step: int):
+        """-> (pinned batch for `step`, slot token to pass to release())."""
+        if step != self._next:
+            raise RuntimeError(f"prefetcher is sequential: expected step {self._next}, got {step}")
+        got_step, slot, buf = self._q.get()
+        if got_step is None:
+            raise buf
+        assert got_step == step
+        self._next += 1
+        return buf, slot
+
+    def release(self, slot: int, event=None) -> None:
+        """Call once the H2D copy of the buffer has been enqueued; `event` (recorded after it) guards reuse."""
+        self._events[slot] = event
+
+    def close(self) -> None:
+        self._halt.set()
+        try:
+            while True:
+                self._q.get_nowait()
+        except Exception:
+            pass
+        self._thread.join(timeout=5)
+
+
 class Trainer:
     def __init__(self, config, for_training: bool = True, synthetic: Optional[bool] = None,
                  run_root: str = "runs", quiet: bool = False, init_params: Optional[Dict[str, torch.Tensor]] = None):
@@ -504,9 +576,19 @@ class Trainer:
 
     # -- one micro-step + (maybe) update; the unit bench.py times ----------------------------------
     def train_step(self, step: int, batch: Optional[torch.Tensor] = None):
-        if batch is None:
-            batch = self.data_manager.generate_batch(step)
-        dev_batch = self._to_device(batch)
+        pf = getattr(self, "_prefetcher", None)
+        if batch is None and pf is not None:
+            pinned, slot = pf.get(step)       # built and staged by the background thread
+            dev_batch = pinned.to(self.device, non_blocking=True)
+            ev = None
+            if self.device.type == "cuda":
+                ev = torch.cuda.Event()
+                ev.record()
+            pf.release(slot, ev)
+        else:
+            if batch is None:
+                batch = self.data_manager.generate_batch(step)
+            dev_batch = self._to_device(batch)
         loss, ntoks = self.compute_loss(self.model, dev_batch[:, :-1], dev_batch[:, 1:])
         loss.backward()
         k = self.grad_accum_steps
@@ -565,6 +647,17 @@ class Trainer:
         start_time = time.time()
         val_loss = None
         last: Dict[str, Any] = {}
+        if os.environ.get("B200_PREFETCH", "1") != "0":
+            self._prefetcher = BatchPrefetcher(self.data_manager.generate_batch, start_step, self.total_steps)
+        try:
+            last = self._train_loop(start_step, total_tokens, log_every, ckpt_every, logf, start_time, val_loss, last)
+        finally:
+            if getattr(self, "_prefetcher", None) is not None:
+                self._prefetcher.close()
+                self._prefetcher = None
+        return last
+
+    def _train_loop(self, start_step, total_tokens, log_every, ckpt_every, logf, start_time, val_loss, last):
         for step in range(start_step, self.total_steps):
             loss, ntoks, did_update = self.train_step(step)
             if did_update:

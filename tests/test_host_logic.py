@@ -160,3 +160,39 @@ def test_tokenizer_byte_level_ids():
     ids = tk.tokenize_doc("hello world, long")
     assert ids[0] == 257 and ids[-1] == 258 and len(ids) == 10
     assert tk.detokenize(ids[1:-1]) == "hello wo"
+
+
+def test_batch_prefetcher_order_reuse_and_errors():
+    """Background batch producer (SURVEY 8f row f4): same batches, in step order, as building them inline;
+    buffers are recycled only after release; producer exceptions surface in the training thread."""
+    import time
+    from mlx_cuda_distributed_pretraining_b200.core.training import BatchPrefetcher
+
+    def make(step):
+        g = torch.Generator().manual_seed(42 + 1000 * step)
+        return torch.randint(0, 100, (4, 9), generator=g, dtype=torch.int64)
+
+    pf = BatchPrefetcher(make, start=3, stop=20, depth=2)
+    seen = []
+    for step in range(3, 20):
+        buf, slot = pf.get(step)
+        assert torch.equal(buf, make(step)), step
+        seen.append(buf.data_ptr())
+        pf.release(slot, None)
+        if step == 5:
+            time.sleep(0.05)          # let the producer run ahead: it must stall at the queue depth
+    assert len(set(seen)) <= 4        # depth + 2 rotating buffers
+    with pytest.raises(RuntimeError):
+        pf.get(7)                     # sequential by construction
+    pf.close()
+
+    def boom(step):
+        if step == 2:
+            raise ValueError("bad document")
+        return make(step)
+
+    pf = BatchPrefetcher(boom, start=0, stop=5)
+    pf.get(0), pf.get(1)
+    with pytest.raises(ValueError):
+        pf.get(2)
+    pf.close()
