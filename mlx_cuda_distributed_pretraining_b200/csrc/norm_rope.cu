@@ -404,12 +404,26 @@ int rmsnorm_fwd_t(const T* x, const T* delta, const T* w, T* sum_out, T* y, floa
                   float eps, cudaStream_t stream) {
   if (H <= RW_MAX_H) {
     const int want = (rows + RW_WARPS - 1) / RW_WARPS;
-    const int grid = want < num_sms() * 8 ? want : num_sms() * 8;
     const int nvw = (H + 255) / 256;
-    if (nvw <= 1) rmsnorm_fwd_warp_kernel<T, 1><<<grid, RN_THREADS, 0, stream>>>(x, delta, w, sum_out, y, rstd, rows, H, eps);
-    else if (nvw <= 2) rmsnorm_fwd_warp_kernel<T, 2><<<grid, RN_THREADS, 0, stream>>>(x, delta, w, sum_out, y, rstd, rows, H, eps);
-    else if (nvw <= 4) rmsnorm_fwd_warp_kernel<T, 4><<<grid, RN_THREADS, 0, stream>>>(x, delta, w, sum_out, y, rstd, rows, H, eps);
-    else rmsnorm_fwd_warp_kernel<T, 8><<<grid, RN_THREADS, 0, stream>>>(x, delta, w, sum_out, y, rstd, rows, H, eps);
+    auto launch = [&](auto kern) -> int {
+      // exactly one resident wave: a second, partial wave of these short CTAs costs ~20 % on a 30 us kernel
+      static int per_sm = 0;
+      if (per_sm == 0) {
+        int n = 0;
+        B200_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, RN_THREADS, 0));
+        per_sm = n > 0 ? n : 1;
+      }
+      const int cap = num_sms() * per_sm;
+      const int grid = want < cap ? want : cap;
+      kern<<<grid, RN_THREADS, 0, stream>>>(x, delta, w, sum_out, y, rstd, rows, H, eps);
+      return B200_OK;
+    };
+    int rc;
+    if (nvw <= 1) rc = launch(rmsnorm_fwd_warp_kernel<T, 1>);
+    else if (nvw <= 2) rc = launch(rmsnorm_fwd_warp_kernel<T, 2>);
+    else if (nvw <= 4) rc = launch(rmsnorm_fwd_warp_kernel<T, 4>);
+    else rc = launch(rmsnorm_fwd_warp_kernel<T, 8>);
+    if (rc) return rc;
     B200_CHECK_LAUNCH();
     return B200_OK;
   }
