@@ -166,6 +166,13 @@ int b200_attn_bwd(const void* q, const void* k, const void* v, const void* o, co
                   const float* lse, void* dq, void* dk, void* dv, int B, int S, int H, int Hk,
                   int D, float scale, int causal, void* workspace, size_t workspace_bytes,
                   void* stream);
+/* Same, with dk / dv token rows of dkv_row_heads heads (>= Hk).  dk = base, dv = base + Hk*D,
+ * dkv_row_heads = 2*Hk writes both into one [B,S,2*Hk*D] buffer, so the k/v projections' dgrad / wgrad
+ * (arch/flash_attention.py:52-53 weights, adjacent in the flat store) each run as ONE GEMM. */
+int b200_attn_bwd_strided(const void* q, const void* k, const void* v, const void* o, const void* d_o,
+                          const float* lse, void* dq, void* dk, void* dv, int B, int S, int H, int Hk,
+                          int D, float scale, int causal, int dkv_row_heads, void* workspace,
+                          size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

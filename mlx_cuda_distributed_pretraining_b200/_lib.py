@@ -51,6 +51,7 @@ SIGNATURES = {
     "b200_attn_bwd_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "b200_attn_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _i,
                            _vp, _sz, _vp]),
+    "b200_attn_bwd_strided": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _i, _i, _vp, _sz, _vp]),
 }
 
 _lib = None

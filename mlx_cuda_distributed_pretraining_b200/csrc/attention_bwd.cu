@@ -25,7 +25,8 @@ int make_bshd_map(CUtensorMap* tm, const void* base, int B, int S, int heads, in
                   bool f32);
 int launch_attn_bwd64(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV,
                       const CUtensorMap& tmDO, const float* lse, const float* delta, float* dq_acc, void* dk,
-                      void* dv, int B, int S, int H, int Hk, float scale, int causal, cudaStream_t stream);
+                      void* dv, int B, int S, int H, int Hk, int dkv_row_heads, float scale, int causal,
+                      cudaStream_t stream);
 
 namespace {
 
@@ -56,9 +57,10 @@ struct BwdArgs {
   const float* lse;    // [B,H,S]
   const float* delta;  // [B,H,S]
   float* dq_acc;       // [B,S,H,D] fp32
-  __nv_bfloat16* dk;   // [B,S,Hk,D]
+  __nv_bfloat16* dk;   // [B,S,Hk,D] rows of dkv_rh heads
   __nv_bfloat16* dv;
   int B, S, H, Hk;
+  int dkv_rh;          // heads per dk/dv token row (>= Hk)
   float scale;
   int causal;
   long long* trace;  // optional clock64 trace of CTA 0 (debug; nullptr in production)
@@ -338,7 +340,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     // dK / dV: the last dq_full commit covers every MMA issued before it
 #pragma unroll 1
     for (int which = 0; which < 2; ++which) {
-      __nv_bfloat16* out = (which == 0 ? p.dv : p.dk) + (((long long)b * p.S + key) * p.Hk + hk) * D;
+      __nv_bfloat16* out = (which == 0 ? p.dv : p.dk) + (((long long)b * p.S + key) * p.dkv_rh + hk) * D;
       const uint32_t col = which == 0 ? Cfg::TM_DV : Cfg::TM_DK;
 #pragma unroll 1
       for (int c0 = wg * (D / 2); c0 < (wg + 1) * (D / 2); c0 += 32) {
@@ -447,7 +449,12 @@ size_t attn_bwd_workspace_bytes(int B, int S, int H, int Hk, int D) {
 
 int attn_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o,
              const float* lse, void* dq, void* dk, void* dv, int B, int S, int H, int Hk, int D,
-             float scale, int causal, void* ws, size_t ws_bytes, cudaStream_t stream) {
+             float scale, int causal, int dkv_row_heads, void* ws, size_t ws_bytes, cudaStream_t stream) {
+  // dk / dv rows may be strided: dkv_row_heads heads per token row (0 = Hk, i.e. contiguous [B,S,Hk,D]).
+  // With dk = base, dv = base + Hk*D and dkv_row_heads = 2*Hk both land in ONE [B,S,2*Hk*D] buffer, which lets
+  // the k/v projections' dgrad and wgrad run as single GEMMs over the concatenated weight.
+  if (dkv_row_heads <= 0) dkv_row_heads = Hk;
+  B200_CHECK_ARG(dkv_row_heads >= Hk, "attn_bwd: dkv_row_heads=%d < Hk=%d", dkv_row_heads, Hk);
   B200_CHECK_ARG(B > 0 && S > 0 && H > 0 && Hk > 0 && H % Hk == 0,
                  "attn_bwd: bad shape B=%d S=%d H=%d Hk=%d", B, S, H, Hk);
   B200_CHECK_ARG(D == 64 || D == 128, "attn_bwd: head_dim %d unsupported (64 or 128)", D);
@@ -486,6 +493,7 @@ int attn_bwd(const void* q, const void* k, const void* v, const void* o, const v
   a.S = S;
   a.H = H;
   a.Hk = Hk;
+  a.dkv_rh = dkv_row_heads;
   a.scale = scale;
   a.causal = causal;
   {
@@ -499,7 +507,8 @@ int attn_bwd(const void* q, const void* k, const void* v, const void* o, const v
   }();
   const bool pipelined64 = D == 64 && !force_v1;
   if (pipelined64)  // software-pipelined head_dim-64 kernel (attention_bwd64.cu)
-    rc = launch_attn_bwd64(tmQ, tmK, tmV, tmDO, lse, delta, dq_acc, dk, dv, B, S, H, Hk, scale, causal, stream);
+    rc = launch_attn_bwd64(tmQ, tmK, tmV, tmDO, lse, delta, dq_acc, dk, dv, B, S, H, Hk, dkv_row_heads, scale, causal,
+                           stream);
   else
     rc = D == 64 ? launch_bwd<64>(tmQ, tmK, tmV, tmDO, a, stream) : launch_bwd<128>(tmQ, tmK, tmV, tmDO, a, stream);
   if (rc) return rc;

@@ -54,6 +54,7 @@ struct Bwd64Args {
   __nv_bfloat16* dk;
   __nv_bfloat16* dv;
   int B, S, H, Hk;
+  int dkv_rh;  // heads per dk/dv token row (>= Hk; 2*Hk when dk and dv share one [B,S,2*Hk*D] buffer)
   float scale;
   int causal;
   long long* trace;  // debug: clock64 stamps of CTA (0,0,0), see tools/attn_trace.py
@@ -386,7 +387,7 @@ attn_bwd64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     // dK / dV; column halves per warpgroup
 #pragma unroll 1
     for (int which = 0; which < 2; ++which) {
-      __nv_bfloat16* out = (which == 0 ? p.dv : p.dk) + (((long long)b * p.S + key) * p.Hk + hk) * D + wg * 32;
+      __nv_bfloat16* out = (which == 0 ? p.dv : p.dk) + (((long long)b * p.S + key) * p.dkv_rh + hk) * D + wg * 32;
       uint32_t v[32];
       tmem_ld_32x32b_x32(t_lane + (which == 0 ? TM_DV : TM_DK) + wg * 32, v);
       tmem_ld_wait();
@@ -422,7 +423,8 @@ int make_bshd_map(CUtensorMap* tm, const void* base, int B, int S, int heads, in
 
 int launch_attn_bwd64(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV,
                       const CUtensorMap& tmDO, const float* lse, const float* delta, float* dq_acc, void* dk,
-                      void* dv, int B, int S, int H, int Hk, float scale, int causal, cudaStream_t stream) {
+                      void* dv, int B, int S, int H, int Hk, int dkv_row_heads, float scale, int causal,
+                      cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
     B200_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
@@ -438,6 +440,7 @@ int launch_attn_bwd64(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUte
   a.S = S;
   a.H = H;
   a.Hk = Hk;
+  a.dkv_rh = dkv_row_heads;
   a.scale = scale;
   a.causal = causal;
   {

@@ -62,7 +62,7 @@ int attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse, i
 size_t attn_bwd_workspace_bytes(int B, int S, int H, int Hk, int D);
 int attn_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o,
              const float* lse, void* dq, void* dk, void* dv, int B, int S, int H, int Hk, int D,
-             float scale, int causal, void* ws, size_t ws_bytes, cudaStream_t stream);
+             float scale, int causal, int dkv_row_heads, void* ws, size_t ws_bytes, cudaStream_t stream);
 }  // namespace b200
 
 #define S_(x) reinterpret_cast<cudaStream_t>(x)
@@ -211,8 +211,15 @@ int b200_attn_bwd(const void* q, const void* k, const void* v, const void* o, co
                   const float* lse, void* dq, void* dk, void* dv, int B, int S, int H, int Hk,
                   int D, float scale, int causal, void* workspace, size_t workspace_bytes,
                   void* stream) {
-  return b200::attn_bwd(q, k, v, o, d_o, lse, dq, dk, dv, B, S, H, Hk, D, scale, causal, workspace,
+  return b200::attn_bwd(q, k, v, o, d_o, lse, dq, dk, dv, B, S, H, Hk, D, scale, causal, 0, workspace,
                         workspace_bytes, S_(stream));
+}
+int b200_attn_bwd_strided(const void* q, const void* k, const void* v, const void* o, const void* d_o,
+                          const float* lse, void* dq, void* dk, void* dv, int B, int S, int H, int Hk,
+                          int D, float scale, int causal, int dkv_row_heads, void* workspace,
+                          size_t workspace_bytes, void* stream) {
+  return b200::attn_bwd(q, k, v, o, d_o, lse, dq, dk, dv, B, S, H, Hk, D, scale, causal, dkv_row_heads,
+                        workspace, workspace_bytes, S_(stream));
 }
 
 }  // extern "C"

@@ -365,6 +365,16 @@ class _MultiLinearFn(torch.autograd.Function):
         x2 = x.reshape(-1, x.shape[-1])
         dx2 = None
         dws = []
+        fused = _fuse_adjacent(dys, ws)   # e.g. (dq, Wq), ([dk | dv], [Wk ; Wv]) when memory layouts allow
+        if fused is not None:
+            for dy2, w, wg in fused:
+                if ctx.needs_input_grad[0]:
+                    if dx2 is None:
+                        dx2 = dy2 @ w
+                    else:
+                        dx2.addmm_(dy2, w)
+                wg.addmm_(dy2.t(), x2)
+            return (dx2.view(x.shape) if dx2 is not None else None, *([None] * len(ws)))
         for i, (dy, w) in enumerate(zip(dys, ws)):
             if dy is None:
                 dws.append(None)
@@ -377,6 +387,42 @@ class _MultiLinearFn(torch.autograd.Function):
                     dx2.addmm_(dy2, w)
             dws.append(_accumulate_wgrad(w, dy2, x2) if ctx.needs_input_grad[1 + i] else None)
         return (dx2.view(x.shape) if dx2 is not None else None, *dws)
+
+
+def _fuse_adjacent(dys, ws):
+    """Backward of projections sharing an input: where two consecutive weights are adjacent in the flat
+    parameter buffer (k_proj / v_proj of a layer), their flat .grad views are adjacent too, and their output
+    gradients are the two column halves of one row-major buffer (attention backward writes dk | dv that way),
+    [dy_a | dy_b] x [W_a ; W_b] is ONE dgrad GEMM and one wgrad GEMM instead of two each.  Returns a list of
+    (dy2 [T, n], W [n, in], W.grad [n, in]) covering all projections, or None when nothing can be merged or
+    some weight's gradient is not a flat-buffer view."""
+    if any(dy is None for dy in dys) or not all(getattr(w, "_b200_flat_grad", False) and w.grad is not None
+                                                 and w.grad.dtype == dy.dtype for w, dy in zip(ws, dys)):
+        return None
+    out, i, merged = [], 0, False
+    while i < len(ws):
+        w, dy = ws[i], dys[i]
+        n, k_in = w.shape
+        es = w.element_size()
+        if i + 1 < len(ws):
+            w2, dy2 = ws[i + 1], dys[i + 1]
+            T = dy.numel() // n
+            rows_ok = all(d.dim() >= 2 and d.shape[-1] == n and d.stride(-1) == 1 and d.stride(-2) == 2 * n and
+                          all(d.stride(j) == d.stride(j + 1) * d.shape[j + 1] for j in range(d.dim() - 2))
+                          for d in (dy, dy2))
+            if (w2.shape == w.shape and w.is_contiguous() and w2.is_contiguous() and rows_ok and
+                    w2.data_ptr() == w.data_ptr() + n * k_in * es and
+                    w2.grad.data_ptr() == w.grad.data_ptr() + n * k_in * es and
+                    dy2.data_ptr() == dy.data_ptr() + n * dy.element_size() and dy2.shape == dy.shape):
+                out.append((torch.as_strided(dy, (T, 2 * n), (2 * n, 1)),
+                            torch.as_strided(w, (2 * n, k_in), (k_in, 1)),
+                            torch.as_strided(w.grad, (2 * n, k_in), (k_in, 1))))
+                i += 2
+                merged = True
+                continue
+        out.append((dy.reshape(-1, n), w, w.grad))
+        i += 1
+    return out if merged else None
 
 
 def linear(x: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
@@ -449,15 +495,17 @@ def attention_bwd_raw(q, k, v, o, do, lse, scale: float, causal: bool):
     B, S, H, D = q.shape
     Hk = k.shape[2]
     dq = torch.empty_like(q)
-    dk = torch.empty_like(k)
-    dv = torch.empty_like(v)
+    # dk and dv share one [B, S, 2*Hk, D] buffer (dk = first Hk heads of every token row, dv = the rest): the
+    # k/v projections' backward can then treat [dk | dv] as ONE matrix against the concatenated weight
+    dkv = torch.empty((B, S, 2 * Hk, D), device=k.device, dtype=k.dtype)
+    dk, dv = dkv[:, :, :Hk], dkv[:, :, Hk:]
     nbytes = int(lib().b200_attn_bwd_workspace_bytes(B, S, H, Hk, D))
     ws = torch.empty(max(nbytes, 16), device=q.device, dtype=torch.uint8)
     tok = _t0("attn_bwd")
-    check(lib().b200_attn_bwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), do.data_ptr(),
-                              lse.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), B, S, H,
-                              Hk, D, float(scale), int(causal), ws.data_ptr(), ws.numel(), _stream()),
-          "b200_attn_bwd")
+    check(lib().b200_attn_bwd_strided(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), do.data_ptr(),
+                                      lse.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), B, S, H,
+                                      Hk, D, float(scale), int(causal), 2 * Hk, ws.data_ptr(), ws.numel(),
+                                      _stream()), "b200_attn_bwd_strided")
     _t1(tok)
     return dq, dk, dv
 

@@ -242,6 +242,41 @@ def test_linear_direct_wgrad(ops):
     assert rel(flat.view(128, 256), 2 * wrs[0].grad) < 6e-3
 
 
+def test_multi_linear_fused_kv_backward(ops):
+    """k/v projections: adjacent weights + [dk | dv] in one buffer -> one dgrad and one wgrad GEMM, same
+    numbers as the separate GEMMs (and as fp32 autograd)."""
+    torch.manual_seed(17)
+    n, k_in, B, S = 64, 128, 2, 48
+    wflat = (torch.randn(2 * n * k_in, device="cuda") * 0.1).to(torch.bfloat16)
+    gflat = torch.zeros_like(wflat)
+    wq = (torch.randn(128, k_in, device="cuda") * 0.1).to(torch.bfloat16).requires_grad_(True)
+    gq = torch.zeros_like(wq)
+    ws = [wq]
+    for i in range(2):
+        w = wflat[i * n * k_in:(i + 1) * n * k_in].view(n, k_in).requires_grad_(True)
+        w.grad = gflat[i * n * k_in:(i + 1) * n * k_in].view(n, k_in)
+        w._b200_flat_grad = True
+        ws.append(w)
+    wq.grad, wq._b200_flat_grad = gq, True
+    x = (torch.randn(B, S, k_in, device="cuda") * 0.5).to(torch.bfloat16).requires_grad_(True)
+    q, k, v = ops.multi_linear(x, ws)
+    dq = torch.randn_like(q)
+    dkv = torch.randn(B, S, 2 * n, device="cuda").to(torch.bfloat16)
+    dk, dv = dkv[..., :n], dkv[..., n:]
+    fused = ops._fuse_adjacent((dq, dk, dv), ws)
+    assert fused is not None and len(fused) == 2 and fused[1][0].shape == (B * S, 2 * n)
+    torch.autograd.backward([q, k, v], [dq, dk, dv])
+    xr = x.detach().float().requires_grad_(True)
+    wr = [w.detach().float().requires_grad_(True) for w in ws]
+    outs = [torch.nn.functional.linear(xr, w) for w in wr]
+    torch.autograd.backward(outs, [dq.float(), dk.float(), dv.float()])
+    assert rel(x.grad, xr.grad) < 6e-3
+    assert rel(gq, wr[0].grad) < 4e-3
+    assert rel(gflat.view(2 * n, k_in), torch.cat([wr[1].grad, wr[2].grad])) < 4e-3
+    # gradients that are NOT two halves of one buffer fall back to per-projection GEMMs
+    assert ops._fuse_adjacent((dq, dk.contiguous(), dv.contiguous()), ws) is None
+
+
 def test_rmsnorm_golden(ops, golden):
     x, w = torch.from_numpy(golden["rms_x"]).cuda(), torch.from_numpy(golden["rms_w"]).cuda()
     assert rel(ops.rmsnorm(x, w, 1e-5), golden["rms_y"]) < 2e-6
