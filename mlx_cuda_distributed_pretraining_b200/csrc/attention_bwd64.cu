@@ -324,18 +324,24 @@ attn_bwd64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         // dS here is P o (dP - delta) WITHOUT the softmax scale: dK and dQ are linear in dS, so the scale is
         // applied once per output element (dK epilogue below, dQ conversion kernel) instead of once per score
         if (!need_mask) {
+          // packed fp32 pairs: exponent argument, dP - delta and the product cost one issue slot per TWO scores
+          const uint64_t sl2_2 = f2_pack(sl2, sl2);
 #pragma unroll
           for (int g = 0; g < 8; ++g) {
             const float4 l4 = *reinterpret_cast<const float4*>(lse2 + c0 + g * 4);
             const float4 d4 = *reinterpret_cast<const float4*>(dlt + c0 + g * 4);
-            const float e0 = ex2f(fmaf(__uint_as_float(vs[g * 4 + 0]), sl2, -l4.x));
-            const float e1 = ex2f(fmaf(__uint_as_float(vs[g * 4 + 1]), sl2, -l4.y));
-            const float e2 = ex2f(fmaf(__uint_as_float(vs[g * 4 + 2]), sl2, -l4.z));
-            const float e3 = ex2f(fmaf(__uint_as_float(vs[g * 4 + 3]), sl2, -l4.w));
-            ds[g * 4 + 0] = e0 * (__uint_as_float(vd[g * 4 + 0]) - d4.x);
-            ds[g * 4 + 1] = e1 * (__uint_as_float(vd[g * 4 + 1]) - d4.y);
-            ds[g * 4 + 2] = e2 * (__uint_as_float(vd[g * 4 + 2]) - d4.z);
-            ds[g * 4 + 3] = e3 * (__uint_as_float(vd[g * 4 + 3]) - d4.w);
+            float a0, a1, a2, a3;
+            f2_unpack(f2_fma(f2_pack(__uint_as_float(vs[g * 4 + 0]), __uint_as_float(vs[g * 4 + 1])), sl2_2,
+                             f2_pack(-l4.x, -l4.y)), a0, a1);
+            f2_unpack(f2_fma(f2_pack(__uint_as_float(vs[g * 4 + 2]), __uint_as_float(vs[g * 4 + 3])), sl2_2,
+                             f2_pack(-l4.z, -l4.w)), a2, a3);
+            const float e0 = ex2f(a0), e1 = ex2f(a1), e2 = ex2f(a2), e3 = ex2f(a3);
+            f2_unpack(f2_mul(f2_pack(e0, e1),
+                             f2_sub(f2_pack(__uint_as_float(vd[g * 4 + 0]), __uint_as_float(vd[g * 4 + 1])),
+                                    f2_pack(d4.x, d4.y))), ds[g * 4 + 0], ds[g * 4 + 1]);
+            f2_unpack(f2_mul(f2_pack(e2, e3),
+                             f2_sub(f2_pack(__uint_as_float(vd[g * 4 + 2]), __uint_as_float(vd[g * 4 + 3])),
+                                    f2_pack(d4.z, d4.w))), ds[g * 4 + 2], ds[g * 4 + 3]);
             pk[g * 2] = pack_bf16x2(e0, e1);
             pk[g * 2 + 1] = pack_bf16x2(e2, e3);
           }
