@@ -196,3 +196,29 @@ def test_batch_prefetcher_order_reuse_and_errors():
     with pytest.raises(ValueError):
         pf.get(2)
     pf.close()
+
+
+def test_fuse_adjacent_detects_only_true_neighbours():
+    """ops._fuse_adjacent (pointer logic, CPU tensors suffice): merges projections whose weights, flat .grad
+    views and output gradients are neighbours in memory, and nothing else."""
+    from mlx_cuda_distributed_pretraining_b200 import ops
+    n, k_in, B, S = 8, 16, 2, 5
+    wflat, gflat = torch.randn(3 * n * k_in), torch.zeros(3 * n * k_in)
+    ws = []
+    for i in range(3):
+        w = wflat[i * n * k_in:(i + 1) * n * k_in].view(n, k_in).requires_grad_(True)
+        w.grad = gflat[i * n * k_in:(i + 1) * n * k_in].view(n, k_in)
+        w._b200_flat_grad = True
+        ws.append(w)
+    packed = torch.randn(B, S, 2 * n)
+    lone = torch.randn(B, S, n)
+    fused = ops._fuse_adjacent((lone, packed[..., :n], packed[..., n:]), ws)
+    assert fused is not None and [f[0].shape for f in fused] == [(B * S, n), (B * S, 2 * n)]
+    assert fused[1][1].data_ptr() == ws[1].data_ptr() and fused[1][1].shape == (2 * n, k_in)
+    assert fused[1][2].data_ptr() == ws[1].grad.data_ptr()
+    assert torch.equal(fused[1][0], packed.view(B * S, 2 * n))
+    # swapped halves, separate buffers, or a weight without a flat gradient: no merge
+    assert ops._fuse_adjacent((lone, packed[..., n:], packed[..., :n]), ws) is None
+    assert ops._fuse_adjacent((lone, torch.randn(B, S, n), torch.randn(B, S, n)), ws) is None
+    ws[2]._b200_flat_grad = False
+    assert ops._fuse_adjacent((lone, packed[..., :n], packed[..., n:]), ws) is None
