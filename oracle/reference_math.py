@@ -3,7 +3,7 @@
 This module is the parity oracle: a literal PyTorch-CPU (fp32, optionally fp64) restatement of the
 arithmetic in arthurcolle/mlx-cuda-distributed-pretraining for the path named in BASELINE.json.
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
-import it; the product package never does (tests/test_no_oracle_in_product.py enforces this).
+import it; the product package never does (tests/test_host_logic.py::test_product_never_imports_oracle).
 
 Pinning status: the reference holds NO golden vectors or numeric asserts for this path (SURVEY.md
 section 4) and its runtime (mlx==0.25.0) is not installable here.  The oracle is pinned instead
