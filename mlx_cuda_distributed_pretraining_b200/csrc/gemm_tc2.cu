@@ -43,6 +43,7 @@ struct Gemm2Args {
   // bytes (full sectors / NVLink flits) instead of 32 rows x 16 bytes.  bf16 output, non-symmetric only.
   int n_peers;
   void* peer_D[7];
+  int staged_epi;  // use the coalescing (smem-transposed) epilogue even without peers
 };
 constexpr int G2_MAX_PEERS = 7;
 
@@ -351,7 +352,7 @@ gemm2_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         tmem_ld_32x32b_x32(t_row + c0, v);
         tmem_ld_wait();
         if constexpr (VEC == 8) {
-          if (p.n_peers > 0) {
+          if (p.n_peers > 0 || p.staged_epi) {
             // ---- fused all-gather path: alpha/beta epilogue -> smem transpose -> coalesced local + peer stores
             const uint32_t stg = epi_stage + (uint32_t)(warp - 4) * 2048u;
 #pragma unroll
@@ -600,6 +601,13 @@ int gemm_bf16_2cta(bool a_mn, bool b_mn, int M, int N, int K, int batch, const v
   a.symmetric = symmetric;
   a.k_splits = k_splits;
   a.ws = splitk_ws;
+  // the coalescing epilogue is also the faster one for plain local stores (8 rows x 64 B per instruction
+  // instead of 32 rows x 16 B: Newton-Schulz chain -3 %); B200_GEMM_STAGED=0 restores direct stores
+  static const bool staged_env = [] {
+    const char* e = getenv("B200_GEMM_STAGED");
+    return !(e != nullptr && e[0] == '0');
+  }();
+  a.staged_epi = (staged_env && !out_f32 && !symmetric && k_splits <= 1) ? 1 : 0;
   a.n_peers = n_peers;
   for (int i = 0; i < G2_MAX_PEERS; ++i) a.peer_D[i] = i < n_peers ? const_cast<void*>(peer_D[i]) : nullptr;
   int rc;
