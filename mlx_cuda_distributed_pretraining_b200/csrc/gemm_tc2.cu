@@ -71,7 +71,7 @@ struct G2Cfg {
   static constexpr int STAGE_BYTES = G2_A_BYTES + B_BYTES;        // per CTA
   static constexpr int STAGES = (BN == 256) ? 6 : 8;
   static constexpr int TMEM_COLS = 2 * BN;
-  static constexpr int EPI_STAGE_BYTES = 8 * 2048;  // 8 epilogue warps x [32 rows x 64 B] transpose tiles
+  static constexpr int EPI_STAGE_BYTES = 8 * 4096;  // 8 epilogue warps x ([32 rows x 64 B] + its transpose for mirror tiles)
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + EPI_STAGE_BYTES;
 };
 
@@ -354,7 +354,8 @@ gemm2_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         if constexpr (VEC == 8) {
           if (p.n_peers > 0 || p.staged_epi) {
             // ---- fused all-gather path: alpha/beta epilogue -> smem transpose -> coalesced local + peer stores
-            const uint32_t stg = epi_stage + (uint32_t)(warp - 4) * 2048u;
+            const uint32_t stg = epi_stage + (uint32_t)(warp - 4) * 4096u;
+            const uint32_t stgT = stg + 2048u;  // [32 columns][32 rows]: the sub-tile transposed (mirror tiles)
 #pragma unroll
             for (int g = 0; g < 32; g += 8) {
               float f[8];
@@ -375,9 +376,22 @@ gemm2_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
               }
               const int piece = g >> 3;
               const uint32_t addr = stg + lane * 64 + (((piece ^ ((lane >> 1) & 3))) << 4);
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pack_bf16x2(f[0], f[1])),
-                           "r"(pack_bf16x2(f[2], f[3])), "r"(pack_bf16x2(f[4], f[5])), "r"(pack_bf16x2(f[6], f[7]))
+              const uint32_t w4[4] = {pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
+                                      pack_bf16x2(f[6], f[7])};
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w4[0]), "r"(w4[1]), "r"(w4[2]),
+                           "r"(w4[3])
                            : "memory");
+              if (mirror) {
+                // transposed copy: element (row = lane, col j) -> [j][lane]; the 32 lanes of one store fill one
+                // 64-byte row of the transposed tile (conflict-free), 16-byte pieces swizzled like the direct tile
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const int j = g + i;
+                  const uint16_t h = (i & 1) ? (uint16_t)(w4[i >> 1] >> 16) : (uint16_t)(w4[i >> 1] & 0xffffu);
+                  const uint32_t ta = stgT + j * 64 + ((((lane >> 3) ^ ((j >> 1) & 3))) << 4) + (lane & 7) * 2;
+                  asm volatile("st.shared.u16 [%0], %1;" ::"r"(ta), "h"(h) : "memory");
+                }
+              }
             }
             __syncwarp();
             const int piece = lane & 3;
@@ -394,6 +408,22 @@ gemm2_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 const long long off = (long long)b * p.strideD + (long long)grow * p.ldd + gn;
                 stg128(reinterpret_cast<OutT*>(p.D) + off, o);
                 for (int pr = 0; pr < p.n_peers; ++pr) stg128(reinterpret_cast<OutT*>(p.peer_D[pr]) + off, o);
+              }
+            }
+            if (mirror) {
+              // D[n0 + c0 + j][m0 + 32 q + 8 piece ..] = transposed sub-tile rows: 8 rows x 64 B per instruction
+              // (the first version issued 32 two-byte stores per lane here)
+              const int mcol = m0 + q * 32 + piece * 8;
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int j = i * 8 + (lane >> 2);
+                uint4 o;
+                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(o.x), "=r"(o.y), "=r"(o.z), "=r"(o.w)
+                             : "r"(stgT + j * 64 + ((piece ^ ((j >> 1) & 3)) << 4)));
+                const int mrow = n0 + c0 + j;
+                if (mrow < p.M && mcol < p.N)
+                  stg128(reinterpret_cast<OutT*>(p.D) + (long long)b * p.strideD + (long long)mrow * p.ldd + mcol, o);
               }
             }
             __syncwarp();
@@ -603,11 +633,13 @@ int gemm_bf16_2cta(bool a_mn, bool b_mn, int M, int N, int K, int batch, const v
   a.ws = splitk_ws;
   // the coalescing epilogue is also the faster one for plain local stores (8 rows x 64 B per instruction
   // instead of 32 rows x 16 B: Newton-Schulz chain -3 %); B200_GEMM_STAGED=0 restores direct stores
-  static const bool staged_env = [] {
+  // 0 = direct stores, 1 = staged everywhere, 2 = staged except symmetric tiles (default: measured A/B on one
+  // box, Newton-Schulz chain 3.62 ms vs 3.66 ms with the transposed-mirror variant, 3.64 -> 3.53 vs mode 0)
+  static const int staged_env = [] {
     const char* e = getenv("B200_GEMM_STAGED");
-    return !(e != nullptr && e[0] == '0');
+    return (e != nullptr && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 2;
   }();
-  a.staged_epi = (staged_env && !out_f32 && !symmetric && k_splits <= 1) ? 1 : 0;
+  a.staged_epi = (staged_env != 0 && !(staged_env == 2 && symmetric) && !out_f32 && k_splits <= 1) ? 1 : 0;
   a.n_peers = n_peers;
   for (int i = 0; i < G2_MAX_PEERS; ++i) a.peer_D[i] = i < n_peers ? const_cast<void*>(peer_D[i]) : nullptr;
   int rc;

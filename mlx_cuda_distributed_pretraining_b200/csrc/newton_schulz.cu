@@ -8,6 +8,8 @@
 // so the reference's transpose for tall matrices (muon.py:68-70,80-81) never materialises, and
 // the normalisation X0 = G/(||G||+eps) is folded into the first iteration's epilogue scalars
 // (per-matrix 1/(norm+eps) vectors produced by the momentum kernel's fused sum of squares).
+#include <stdlib.h>
+
 #include "host.h"
 
 namespace b200 {
@@ -43,7 +45,10 @@ static int g1_k_splits(int batch, int m, int k) {
 
 // A = X X^T and B = bA + cAA are symmetric: only tiles on or above the diagonal are computed and
 // the rest mirror-written (force_bn code understood by gemm_bf16; ignored when it cannot apply)
-static constexpr int kSym = 1256;
+static const int kSym = [] {
+  const char* e = getenv("B200_NS_NOSYM");  // debug: full (non-symmetric) G1/G2 tiles
+  return (e != nullptr && e[0] == '1') ? 0 : 1256;
+}();
 
 size_t newton_schulz_workspace_bytes(int batch, int rows, int cols, int steps) {
   const size_t m = rows < cols ? rows : cols;
