@@ -18,6 +18,9 @@ What is exercised (reference file:line):
   arch/flash_attention.py:78-194 FlashAttention._flash_attention and __call__ (MHA/GQA/MQA, causal)
   arch/llama.py:44-56,142-151,322-412 RMSNorm, MLP, Model.__call__ (tiny config, tied embeddings)
   mlx_lm_utils.py:5-56         linear_schedule / cosine_decay / join_schedules
+  distributed/hybrid_distributed.py:303-354,430-452  HybridDeviceManager._aggregate_gradients /
+                               distribute_batch (the data-parallel contract: unweighted mean, remainder
+                               rows to the last shard)
 """
 import os
 import sys
@@ -149,6 +152,27 @@ joined = ref_sched.join_schedules([warm, cos], [10])
 steps = np.array([0, 1, 5, 9, 10, 11, 50, 109, 110, 500])
 out["sched_steps"] = steps
 out["sched_values"] = np.array([float(joined(int(s))) for s in steps], dtype=np.float64)
+
+# ---- data-parallel contract -------------------------------------------------------------------------
+from distributed.hybrid_distributed import HybridDeviceManager  # noqa: E402
+
+
+class _Devices:  # distribute_batch only looks at the device names
+    device_queues = {"mlx:0": None, "cuda:0": None, "cuda:1": None}
+
+
+dp_batch = rng.integers(0, 100, size=(10, 6)).astype(np.int64)
+out["dp_batch"] = dp_batch
+for i, (_, sub) in enumerate(HybridDeviceManager.distribute_batch(_Devices(), mx.array(dp_batch))):
+    out[f"dp_shard_{i}"] = np.asarray(sub)
+dp_grads = [{"w": f32(4, 5), "b": f32(7)} for _ in range(3)]
+for i, gd in enumerate(dp_grads):
+    for k, v in gd.items():
+        out[f"dp_grad_{i}_{k}"] = v
+# _aggregate_gradients accumulates IN PLACE into the first worker's arrays: hand it copies
+agg = HybridDeviceManager._aggregate_gradients(None, [{k: mx.array(v.copy()) for k, v in gd.items()} for gd in dp_grads])
+for k, v in agg.items():
+    out[f"dp_mean_{k}"] = np.asarray(v)
 
 np.savez_compressed(HERE / "reference_vectors.npz", **out)
 print(f"wrote {HERE / 'reference_vectors.npz'} with {len(out)} arrays")

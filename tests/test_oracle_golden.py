@@ -123,6 +123,24 @@ def test_newton_schulz_properties():
         assert rel(R.newton_schulz5(G.T).numpy(), X.T.numpy()) < 1e-5
 
 
+def test_dp_contract_matches_reference(golden):
+    """distributed/hybrid_distributed.py:303-354 (_aggregate_gradients) and :430-452 (distribute_batch), run
+    from the reference's own source: unweighted mean over workers, remainder rows to the last shard -- for the
+    oracle AND for the product's host-side helper."""
+    from mlx_cuda_distributed_pretraining_b200.distributed import dp
+    per_dev = [{k: torch.from_numpy(golden[f"dp_grad_{i}_{k}"]) for k in ("w", "b")} for i in range(3)]
+    mean = R.mean_gradients(per_dev)
+    for k in ("w", "b"):
+        assert rel(mean[k].numpy(), golden[f"dp_mean_{k}"]) < 1e-6
+    batch = torch.from_numpy(golden["dp_batch"])
+    for r in range(3):
+        assert torch.equal(dp.shard_batch(batch, r, 3), torch.from_numpy(golden[f"dp_shard_{r}"]))
+    # the CUDA path reaches the same mean as sum-all-reduce * (1/world) folded into the optimizer's gradient scale
+    flat_sum = sum(torch.cat([d["w"].flatten(), d["b"]]) for d in per_dev)
+    want = torch.cat([torch.from_numpy(golden["dp_mean_w"]).flatten(), torch.from_numpy(golden["dp_mean_b"])])
+    assert rel((flat_sum * (1.0 / 3)).numpy(), want.numpy()) < 1e-6
+
+
 def test_dp_contract():
     g = [{"w": torch.ones(2, 2) * i} for i in (1.0, 3.0)]
     assert torch.equal(R.mean_gradients(g)["w"], torch.ones(2, 2) * 2.0)
