@@ -18,6 +18,11 @@ What is exercised (reference file:line):
   arch/flash_attention.py:78-194 FlashAttention._flash_attention and __call__ (MHA/GQA/MQA, causal)
   arch/llama.py:44-56,142-151,322-412 RMSNorm, MLP, Model.__call__ (tiny config, tied embeddings)
   mlx_lm_utils.py:5-56         linear_schedule / cosine_decay / join_schedules
+  core/training.py:324-543     TokenizerManager (byte level) and DataManager (chunking, length sort, shuffles,
+                               padded batches, validation walk) on tests/golden/tiny_corpus.jsonl, seeded as
+                               Trainer.setup_system does (:966-968)
+  core/training.py:764-856     OptimizationManager.create_scheduler (all three types) and the Shampoo branch of
+                               create_optimizer (factory defaults -> ShampooParams)
   distributed/hybrid_distributed.py:303-354,430-452  HybridDeviceManager._aggregate_gradients /
                                distribute_batch (the data-parallel contract: unweighted mean, remainder
                                rows to the last shard)
@@ -173,6 +178,52 @@ for i, gd in enumerate(dp_grads):
 agg = HybridDeviceManager._aggregate_gradients(None, [{k: mx.array(v.copy()) for k, v in gd.items()} for gd in dp_grads])
 for k, v in agg.items():
     out[f"dp_mean_{k}"] = np.asarray(v)
+
+# ---- tokenizer + data path (core/training.py:324-543) ----------------------------------------------
+import contextlib  # noqa: E402
+import io  # noqa: E402
+import random as _random  # noqa: E402
+
+import core.training as ref_training  # noqa: E402
+
+data_cfg = ref_training.DataConfig(
+    input_file=str(HERE / "tiny_corpus.jsonl"), validation_file=str(HERE / "tiny_val.jsonl"),
+    preprocessing={"max_context_size": 96, "chunk_overlap": 16},
+    tokenizer={"normal_vocab_size": 256, "special_tokens": {"pad": "<pad>", "bos": "<bos>", "eos": "<eos>"}})
+_random.seed(42)
+np.random.seed(42)
+tok = ref_training.TokenizerManager(data_cfg)
+with contextlib.redirect_stdout(io.StringIO()):          # _create_batch prints every batch shape
+    dm = ref_training.DataManager(data_cfg, tok, batch_size=3)
+    out["data_special"] = np.array([tok.PAD_TOKEN, tok.BOS_TOKEN, tok.EOS_TOKEN, tok.VOCAB_SIZE], dtype=np.int64)
+    out["data_num_docs"] = np.array([len(dm.train_docs), len(dm.val_docs), len(dm.train_batch_idx),
+                                     dm.num_validation_batches], dtype=np.int64)
+    out["data_tokenize_doc"] = np.array(tok.tokenize_doc("naïve 東京 ok"), dtype=np.int64)
+    for step in range(8):
+        out[f"data_batch_{step}"] = np.asarray(dm.generate_batch(step)).astype(np.int64)
+    for i in range(3):
+        out[f"data_val_{i}"] = np.asarray(dm.generate_validation_batch(i)).astype(np.int64)
+
+# ---- scheduler composition and the Shampoo factory defaults (core/training.py:764-856) -------------------
+import dataclasses  # noqa: E402
+
+
+def _tc(scheduler, optimization, lr=1e-2, iters=8000):
+    return ref_training.TrainingConfig(hyperparameters={"batch_size": 16, "learning_rate": lr, "weight_decay": 0.01,
+                                                        "iters": iters}, scheduler=scheduler, optimization=optimization)
+
+
+om_steps = np.array([0, 1, 10, 799, 800, 801, 2500, 4000, 7999, 8000, 8799, 9500])
+out["om_steps"] = om_steps
+for tag, sc in (("warmcos", {"type": "cosine_with_warmup", "min_lr_ratio": 0.05, "warmup_steps": 800}),
+                ("cos", {"type": "cosine", "min_lr_ratio": 0.01}), ("lin", {"type": "linear"})):
+    sched_fn = ref_training.OptimizationManager(_tc(sc, {"optimizer": "adamw"}), 8000).create_scheduler()
+    out[f"om_sched_{tag}"] = np.array([float(sched_fn(int(s))) for s in om_steps], dtype=np.float64)
+sh = ref_training.OptimizationManager(_tc({"type": "cosine", "min_lr_ratio": 0.1}, {"optimizer": "shampoo"}, lr=1e-3),
+                                      5000)
+sh_opt = sh.create_optimizer(sh.create_scheduler())       # every Shampoo knob left to the factory's default
+for k, v in dataclasses.asdict(sh_opt.params).items():
+    out[f"om_shampoo::{k}"] = np.array(v)
 
 np.savez_compressed(HERE / "reference_vectors.npz", **out)
 print(f"wrote {HERE / 'reference_vectors.npz'} with {len(out)} arrays")

@@ -141,6 +141,62 @@ def test_dp_contract_matches_reference(golden):
     assert rel((flat_sum * (1.0 / 3)).numpy(), want.numpy()) < 1e-6
 
 
+def test_tokenizer_and_data_path_match_reference(golden):
+    """core/training.py:324-543 run from the reference's own source on tests/golden/tiny_corpus.jsonl: byte-level
+    special-token ids, document chunking with overlap, length-sorted + shuffled batch order (same global RNG
+    calls under the seeds Trainer.setup_system sets), padding / truncation, and the validation walk."""
+    import random
+    import numpy as np
+    from pathlib import Path
+    from mlx_cuda_distributed_pretraining_b200.core.training import DataConfig, DataManager, TokenizerManager
+    here = Path(__file__).resolve().parent / "golden"
+    cfg = DataConfig(input_file=str(here / "tiny_corpus.jsonl"), validation_file=str(here / "tiny_val.jsonl"),
+                     preprocessing={"max_context_size": 96, "chunk_overlap": 16},
+                     tokenizer={"normal_vocab_size": 256,
+                                "special_tokens": {"pad": "<pad>", "bos": "<bos>", "eos": "<eos>"}})
+    random.seed(42)
+    np.random.seed(42)
+    tok = TokenizerManager(cfg)
+    dm = DataManager(cfg, tok, batch_size=3)
+    assert [tok.PAD_TOKEN, tok.BOS_TOKEN, tok.EOS_TOKEN, tok.VOCAB_SIZE] == golden["data_special"].tolist()
+    assert [len(dm.train_docs), len(dm.val_docs), len(dm.train_batch_idx), dm.num_validation_batches] == \
+        golden["data_num_docs"].tolist()
+    assert tok.tokenize_doc("naïve 東京 ok") == golden["data_tokenize_doc"].tolist()
+    for step in range(8):
+        assert torch.equal(dm.generate_batch(step), torch.from_numpy(golden[f"data_batch_{step}"])), step
+    for i in range(3):
+        assert torch.equal(dm.generate_validation_batch(i), torch.from_numpy(golden[f"data_val_{i}"])), i
+    assert tok.detokenize(golden["data_tokenize_doc"][1:-1]) == "naïve 東京 ok"
+
+
+def test_scheduler_and_shampoo_factory_match_reference(golden):
+    """core/training.py:764-856 run from the reference's own OptimizationManager: the three scheduler types as
+    composed there (cosine sees step - warmup, total_steps not reduced by the warm-up) and the ShampooParams the
+    factory builds when the YAML leaves every knob at its default -- for the oracle and for the product."""
+    import dataclasses
+    from mlx_cuda_distributed_pretraining_b200.core.training import OptimizationManager, TrainingConfig
+    steps = golden["om_steps"]
+
+    def tc(scheduler, optimization, lr=1e-2, iters=8000):
+        return TrainingConfig(hyperparameters={"batch_size": 16, "learning_rate": lr, "weight_decay": 0.01,
+                                               "iters": iters}, scheduler=scheduler, optimization=optimization)
+
+    for tag, sc in (("warmcos", {"type": "cosine_with_warmup", "min_lr_ratio": 0.05, "warmup_steps": 800}),
+                    ("cos", {"type": "cosine", "min_lr_ratio": 0.01}), ("lin", {"type": "linear"})):
+        fn = OptimizationManager(tc(sc, {"optimizer": "adamw"}), 8000).create_scheduler()
+        got = np.array([float(fn(int(s))) for s in steps])
+        assert np.allclose(got, golden[f"om_sched_{tag}"], rtol=1e-6, atol=1e-12), tag
+    want = golden["om_sched_warmcos"]
+    sched = R.make_schedule({"type": "cosine_with_warmup", "min_lr_ratio": 0.05, "warmup_steps": 800}, 1e-2, 8000)
+    assert np.allclose([sched(int(s)) for s in steps], want, rtol=1e-6, atol=1e-12)
+    om = OptimizationManager(tc({"type": "cosine", "min_lr_ratio": 0.1}, {"optimizer": "shampoo"}, lr=1e-3), 5000)
+    params = dataclasses.asdict(om.create_optimizer(om.create_scheduler()).params)
+    ref = {k.split("::", 1)[1]: golden[k] for k in golden.files if k.startswith("om_shampoo::")}
+    assert set(params) == set(ref)
+    for k, v in params.items():
+        assert str(v) == str(ref[k].item()) or float(v) == float(ref[k]), (k, v, ref[k])
+
+
 def test_dp_contract():
     g = [{"w": torch.ones(2, 2) * i} for i in (1.0, 3.0)]
     assert torch.equal(R.mean_gradients(g)["w"], torch.ones(2, 2) * 2.0)
