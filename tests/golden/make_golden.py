@@ -21,6 +21,7 @@ What is exercised (reference file:line):
   core/training.py:324-543     TokenizerManager (byte level) and DataManager (chunking, length sort, shuffles,
                                padded batches, validation walk) on tests/golden/tiny_corpus.jsonl, seeded as
                                Trainer.setup_system does (:966-968)
+  core/training.py:1195-1234   Trainer.compute_loss (masked token-mean cross-entropy) on the tiny Model
   core/training.py:764-856     OptimizationManager.create_scheduler (all three types) and the Shampoo branch of
                                create_optimizer (factory defaults -> ShampooParams)
   distributed/hybrid_distributed.py:303-354,430-452  HybridDeviceManager._aggregate_gradients /
@@ -203,6 +204,25 @@ with contextlib.redirect_stdout(io.StringIO()):          # _create_batch prints 
         out[f"data_batch_{step}"] = np.asarray(dm.generate_batch(step)).astype(np.int64)
     for i in range(3):
         out[f"data_val_{i}"] = np.asarray(dm.generate_validation_batch(i)).astype(np.int64)
+
+# ---- Trainer.compute_loss (core/training.py:1195-1234) on the tiny model above --------------------------
+import logging  # noqa: E402
+import types  # noqa: E402
+
+PAD = 66
+loss_batch = rng.integers(0, 66, size=(3, 13)).astype(np.int64)
+loss_batch[0, 9:] = PAD          # padded tails, as DataManager._create_batch produces them
+loss_batch[2, 5:] = PAD
+_self = types.SimpleNamespace(
+    logger=logging.getLogger("golden"), distributed=False, device_mgr=None,
+    config=types.SimpleNamespace(model=types.SimpleNamespace(
+        attention={"num_heads": 4, "head_dim": 16, "max_position_embeddings": 64}, dimensions={"hidden_size": 64})),
+    mixed_precision=ref_training.MixedPrecisionManager(False), tokenizer=types.SimpleNamespace(PAD_TOKEN=PAD))
+loss_val, loss_ntoks = ref_training.Trainer.compute_loss(_self, model, mx.array(loss_batch[:, :-1]),
+                                                          mx.array(loss_batch[:, 1:]))
+out["loss_batch"] = loss_batch
+out["loss_value"] = np.array(float(loss_val), dtype=np.float64)
+out["loss_ntoks"] = np.array(int(loss_ntoks), dtype=np.int64)
 
 # ---- scheduler composition and the Shampoo factory defaults (core/training.py:764-856) -------------------
 import dataclasses  # noqa: E402

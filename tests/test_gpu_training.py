@@ -223,6 +223,31 @@ def test_checkpoint_roundtrip_and_log_format(tmp_path):
     assert tr2.optimizer.count == 3
 
 
+@pytest.mark.parametrize("mixed", [False, True])
+def test_model_and_loss_match_reference_golden(tmp_path, mixed):
+    """The product model + Trainer.compute_loss against what the REFERENCE's own arch/llama.py and
+    core/training.py:1195-1234 produced for the same weights and tokens (tests/golden/make_golden.py)."""
+    import numpy as np
+    from mlx_cuda_distributed_pretraining_b200.core.training import Config, Trainer
+    g = np.load(ROOT / "tests" / "golden" / "reference_vectors.npz")
+    cfg = tiny_config(optimizer="adamw", mixed=mixed)
+    cfg["data"]["tokenizer"]["normal_vocab_size"] = 64                     # 64 + pad/bos/eos = the golden model's 67
+    cfg["model"]["dimensions"] = {"hidden_size": 64, "intermediate_size": 96, "num_layers": 2}
+    cfg["model"]["attention"] = {"num_heads": 4, "num_kv_heads": 2, "head_dim": 16, "max_position_embeddings": 64}
+    params = {k.split("::", 1)[1]: torch.from_numpy(g[k]) for k in g.files if k.startswith("model_param::")}
+    tr = Trainer(Config.from_dict(cfg), synthetic=True, quiet=True, run_root=str(tmp_path), init_params=params)
+    tokens = torch.from_numpy(g["model_tokens"]).cuda()
+    with torch.no_grad():
+        logits = tr.model(tokens).float()
+    assert rel(logits, torch.from_numpy(g["model_logits"])) < (2e-2 if mixed else 5e-3)
+    tr.tokenizer.PAD_TOKEN = 66                                            # the pad id the golden batch uses
+    batch = torch.from_numpy(g["loss_batch"]).cuda()
+    with torch.no_grad():
+        loss, ntoks = tr.compute_loss(tr.model, batch[:, :-1], batch[:, 1:])
+    assert int(ntoks) == int(g["loss_ntoks"])
+    assert abs(float(loss) - float(g["loss_value"])) < (3e-2 if mixed else 5e-3)
+
+
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
 def test_two_gpu_data_parallel_matches_mean_of_gradients(tmp_path):
     """2 ranks x batch 2 (NCCL all-reduce of the flat gradient buffer, 1/world folded into the

@@ -105,6 +105,18 @@ def test_llama_forward_matches_reference(golden):
     assert rel(logits.numpy(), golden["model_logits"]) < 5e-5
 
 
+def test_compute_loss_matches_reference(golden):
+    """Trainer.compute_loss (core/training.py:1195-1234) called from the reference's source on the tiny model:
+    fp32 cross-entropy, PAD-masked, summed and divided by the number of real tokens."""
+    params = _model_params(golden)
+    d = R.LlamaDims(64, 96, 2, 4, 2, 16, 67)
+    batch = t(golden["loss_batch"])
+    logits = R.llama_forward(params, batch[:, :-1], d)
+    loss, ntoks = R.compute_loss(logits, batch[:, 1:], pad_token=66)
+    assert int(ntoks) == int(golden["loss_ntoks"])
+    assert abs(float(loss) - float(golden["loss_value"])) < 2e-5
+
+
 def test_schedule_matches_reference(golden):
     sched = R.make_schedule({"type": "cosine_with_warmup", "warmup_steps": 10, "min_lr_ratio": 0.1}, 3e-4, 100)
     got = np.array([sched(int(s)) for s in golden["sched_steps"]])
