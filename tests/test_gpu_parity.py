@@ -137,6 +137,33 @@ def test_muon_momentum_and_scales(ops, gdt):
     assert rel(inv, 1 / (ss.sqrt() + 1e-7)) < 1e-6 and rel(inv2, inv * inv) < 1e-6
 
 
+def test_muon_update_golden(ops, golden):
+    """The product's Muon.update(model, gradients) -- momentum, Nesterov, Newton-Schulz on tcgen05, scaled apply,
+    SGD-momentum fallback for the 1-D parameter -- against two steps of the REFERENCE's own optimizers/muon.py
+    (callable learning rate, explicit gradient dict, as the reference trainer calls it)."""
+    from mlx_cuda_distributed_pretraining_b200.optimizers.muon import Muon
+    names = ("w_wide", "w_tall", "gain")
+
+    class Tiny(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            for k in names:
+                setattr(self, k, torch.nn.Parameter(torch.from_numpy(golden[f"muon_param_{k}"]).clone()))
+
+    model = Tiny().cuda()
+    opt = Muon(learning_rate=lambda step: 0.01 * (step + 1), momentum=0.95, nesterov=True, ns_steps=5)
+    for step in range(2):
+        before = {k: getattr(model, k).detach().clone() for k in names}
+        opt.update(model, {k: torch.from_numpy(golden[f"muon_s{step}_grad_{k}"]).cuda() for k in names})
+        for k in names:
+            upd = getattr(model, k).detach() - before[k]
+            # 2-D updates go through bf16-operand Newton-Schulz (3e-2, like test_newton_schulz_golden); the 1-D one
+            # is plain fp32 arithmetic
+            assert rel(upd, golden[f"muon_s{step}_upd_{k}"]) < (3e-2 if upd.dim() == 2 else 1e-5), (step, k)
+            assert rel(opt.state[k]["momentum_buffer"], golden[f"muon_s{step}_buf_{k}"]) < 1e-6, (step, k)
+    assert opt.count == 2
+
+
 def test_adamw_sgd_axpy_clip(ops):
     torch.manual_seed(4)
     n = 4099
