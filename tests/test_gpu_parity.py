@@ -164,6 +164,26 @@ def test_muon_update_golden(ops, golden):
     assert opt.count == 2
 
 
+def test_shampoo_statistics_golden(ops, golden):
+    """The product Shampoo's Kronecker-factor statistics after two updates (EMA of G G^T and G^T G over the
+    top-left 32 x 32 block, beta2 = 0.95) against the REFERENCE's own Shampoo._update_statistics."""
+    from mlx_cuda_distributed_pretraining_b200.optimizers.shampoo import Shampoo, ShampooParams
+
+    class Tiny(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.w = torch.nn.Parameter(torch.zeros(48, 40))
+
+    model = Tiny().cuda()
+    opt = Shampoo(learning_rate=0.01, params=ShampooParams(beta2=0.95, start_preconditioning_step=1000,
+                                                           update_period=1, max_preconditioner_dim=32))
+    for k in ("sh_g1", "sh_g2"):
+        opt.update(model, {"w": torch.from_numpy(golden[k]).cuda()})
+    # the factor products run on bf16 operands (gradients are bf16 on the training path), fp32 accumulation
+    assert rel(opt.state["w"]["statistics.0"], golden["sh_stat0"]) < 1e-2
+    assert rel(opt.state["w"]["statistics.1"], golden["sh_stat1"]) < 1e-2
+
+
 def test_adamw_sgd_axpy_clip(ops):
     torch.manual_seed(4)
     n = 4099
