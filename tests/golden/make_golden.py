@@ -24,6 +24,7 @@ What is exercised (reference file:line):
   core/training.py:1195-1234   Trainer.compute_loss (masked token-mean cross-entropy) on the tiny Model
   core/training.py:764-856     OptimizationManager.create_scheduler (all three types) and the Shampoo branch of
                                create_optimizer (factory defaults -> ShampooParams)
+  core/training.py:52-166      Config.from_yaml on this repo's configs/c*.yaml -> tests/golden/ref_config_parse.json
   distributed/hybrid_distributed.py:303-354,430-452  HybridDeviceManager._aggregate_gradients /
                                distribute_batch (the data-parallel contract: unweighted mean, remainder
                                rows to the last shard)
@@ -244,6 +245,12 @@ sh = ref_training.OptimizationManager(_tc({"type": "cosine", "min_lr_ratio": 0.1
 sh_opt = sh.create_optimizer(sh.create_scheduler())       # every Shampoo knob left to the factory's default
 for k, v in dataclasses.asdict(sh_opt.params).items():
     out[f"om_shampoo::{k}"] = np.array(v)
+
+# ---- YAML schema: this repo's configs/*.yaml parsed by the REFERENCE's Config dataclasses (core/training.py:52-166)
+import json  # noqa: E402
+
+ref_cfg = {p.name: dataclasses.asdict(ref_training.Config.from_yaml(str(p))) for p in sorted((REPO / "configs").glob("c*.yaml"))}
+(HERE / "ref_config_parse.json").write_text(json.dumps(ref_cfg, indent=1, sort_keys=True) + "\n")
 
 np.savez_compressed(HERE / "reference_vectors.npz", **out)
 print(f"wrote {HERE / 'reference_vectors.npz'} with {len(out)} arrays")

@@ -222,3 +222,29 @@ def test_fuse_adjacent_detects_only_true_neighbours():
     assert ops._fuse_adjacent((lone, torch.randn(B, S, n), torch.randn(B, S, n)), ws) is None
     ws[2]._b200_flat_grad = False
     assert ops._fuse_adjacent((lone, packed[..., :n], packed[..., n:]), ws) is None
+
+
+def test_yaml_schema_matches_reference_parse():
+    """configs/c*.yaml parsed by the REFERENCE's own Config dataclasses (tests/golden/ref_config_parse.json,
+    written by tests/golden/make_golden.py) vs this repo's Config: every section / key / default the reference
+    sees must come out identical here, so a YAML written for the reference runs unchanged."""
+    import dataclasses
+    import json
+    from mlx_cuda_distributed_pretraining_b200.core.training import Config
+    ref = json.loads((ROOT / "tests" / "golden" / "ref_config_parse.json").read_text())
+    assert len(ref) == 5
+
+    def subset(a, b, path):
+        if isinstance(a, dict):
+            assert isinstance(b, dict), path
+            for k, v in a.items():
+                assert k in b, f"{path}.{k} missing"
+                subset(v, b[k], f"{path}.{k}")
+        elif isinstance(a, list):
+            assert list(b) == a, path
+        else:
+            assert a == b, (path, a, b)
+
+    for name, want in ref.items():
+        got = dataclasses.asdict(Config.from_yaml(str(ROOT / "configs" / name)))
+        subset(want, got, name)
