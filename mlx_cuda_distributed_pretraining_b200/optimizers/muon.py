@@ -116,6 +116,14 @@ class Muon:
             self._alloc_gather_buffers(store, world)
         p2p = world > 1 and self._xg_handles is not None
         pending = []
+        # experimental (B200_NS_STREAMS=2, single process): run the shape groups' chains alternately on two
+        # side streams so that one group's tail wave is filled by the other group's tiles
+        n_streams = int(os.environ.get("B200_NS_STREAMS", "1")) if world == 1 else 1
+        if n_streams > 1:
+            self._update_multistream(store, gsrc, lr, lib, a, b, c, n_streams)
+            self._update_vectors(store, gsrc, lr)
+            self.count += 1
+            return
         for gi, g in enumerate(store.mat_groups):
             n = g.numel
             rc = g.rows * g.cols
@@ -175,6 +183,10 @@ class Muon:
                 if w is not None:
                     w.wait()   # orders the current stream after the collective
             self._apply(store, g, x, lr, lib, stream)
+        self._update_vectors(store, gsrc, lr)
+        self.count += 1
+
+    def _update_vectors(self, store, gsrc, lr) -> None:
         if store.vec_end > store.vec_offset:
             lo, hi = store.vec_offset, store.vec_end
             if self.alternate_optimizer is not None:
@@ -183,7 +195,40 @@ class Muon:
                 p16 = store.shadow[lo:hi] if store.mixed else None
                 ops.sgd_momentum(store.master[lo:hi], p16, gsrc[lo:hi], self._buf[lo:hi], self.momentum,
                                  self.nesterov, lr, self.grad_scale)
-        self.count += 1
+
+    def _update_multistream(self, store, gsrc, lr, lib, a, b, c, n_streams: int) -> None:
+        main = torch.cuda.current_stream()
+        if getattr(self, "_side", None) is None or len(self._side) != n_streams:
+            self._side = [torch.cuda.Stream(device=store.device) for _ in range(n_streams)]
+            self._side_bufs = [tuple(torch.empty_like(t) for t in (self._u, self._x, self._ws, self._ss, self._inv, self._inv2))
+                               for _ in range(n_streams)]
+        fork = torch.cuda.Event()
+        fork.record(main)
+        tok = ops._t0("newton_schulz")   # spans the whole forked region on the main stream
+        for st in self._side:
+            st.wait_event(fork)
+        for gi, g in enumerate(store.mat_groups):
+            st = self._side[gi % n_streams]
+            u_, x_, ws_, ss_, inv_, inv2_ = self._side_bufs[gi % n_streams]
+            n, rc = g.numel, g.rows * g.cols
+            gg = gsrc[g.offset:g.offset + n]
+            buf = self._buf[g.offset:g.offset + n]
+            with torch.cuda.stream(st):
+                sp = ops._stream()
+                ops.check(lib.b200_muon_momentum(gg.data_ptr(), ops._is_bf16(gg, "grad"), buf.data_ptr(), u_.data_ptr(),
+                                                 ss_.data_ptr(), rc, g.batch, float(self.momentum), int(self.nesterov),
+                                                 float(self.grad_scale), sp), "b200_muon_momentum")
+                ops.check(lib.b200_ns_scales(ss_.data_ptr(), inv_.data_ptr(), inv2_.data_ptr(), g.batch, ops.NS_EPS, sp),
+                          "b200_ns_scales")
+                ops.check(lib.b200_newton_schulz(u_.data_ptr(), x_.data_ptr(), g.batch, g.rows, g.cols, self.ns_steps,
+                                                 a, b, c, inv_.data_ptr(), inv2_.data_ptr(), ws_.data_ptr(), ws_.numel(),
+                                                 sp), "b200_newton_schulz")
+                self._apply(store, g, x_, lr, lib, sp)
+        for st in self._side:
+            ev = torch.cuda.Event()
+            ev.record(st)
+            main.wait_event(ev)
+        ops._t1(tok)
 
     def _alloc_gather_buffers(self, store, world: int) -> None:
         """One padded buffer per shape group: world * ceil(batch/world) matrices, so exchanges can stay in
