@@ -42,6 +42,8 @@ unsigned long long b200_launch_count(void); /* kernels launched by this library 
  * alpha_vec/beta_vec: optional per-batch device scalars (NULL = 1).
  * force_bn: 0 auto | 128 | 256 tile width | 1256 = 256-wide tiles and the caller asserts D == D^T
  * (M == N, bf16 out): only tiles on/above the diagonal are computed, the rest mirror-written.
+ * lda/ldb/ldd/ldc multiples of 8 (bf16) / 4 (f32 C,D).  M, K arbitrary (TMA zero-fills); N arbitrary too if
+ * ldd/ldc >= round_up(N, 16 bytes): the padded tail columns of D are then written with alpha*0 + beta*C.
  */
 int b200_gemm_bf16(int a_mn, int b_mn, int M, int N, int K, int batch,
                    const void* A, long long lda, long long strideA,
@@ -72,12 +74,15 @@ int b200_newton_schulz_allgather(const void* x_in, void* x_out, int batch, int r
                                  const float* inv_norm_sq, void* workspace, size_t workspace_bytes,
                                  const void* const* peer_out, int n_peers, void* stream);
 
+/* Scratch of the grid reductions below (b200_muon_momentum, b200_sumsq): per-block partials + arrival
+ * counters.  The reductions are DETERMINISTIC (fixed summation order, no float atomics), so data-parallel
+ * replicas that hold identical gradients compute bit-identical norms and stay bit-identical. */
+size_t b200_reduce_workspace_bytes(int batch);
 /* muon.py:101,105: buf = (1-mu)*g*gscale + mu*buf ; u = nesterov ? g*gscale + mu*buf : buf.
- * g: [batch,numel] bf16 (g_is_bf16=1) or f32; buf f32; u bf16; sumsq[b] = sum(u_b^2) (zeroed
- * inside). */
+ * g: [batch,numel] bf16 (g_is_bf16=1) or f32; buf f32; u bf16; sumsq[b] = sum(u_b^2) (overwritten). */
 int b200_muon_momentum(const void* g, int g_is_bf16, float* buf, void* u_bf16, float* sumsq,
                        long long numel, int batch, float mu, int nesterov, float gscale,
-                       void* stream);
+                       void* workspace, size_t workspace_bytes, void* stream);
 /* muon.py:72-73: inv_norm = 1/(sqrt(sumsq)+eps), inv_norm_sq = inv_norm^2 */
 int b200_ns_scales(const float* sumsq, float* inv_norm, float* inv_norm_sq, int batch, float eps,
                    void* stream);
@@ -104,9 +109,10 @@ int b200_adam_direction(float* d, const void* g, int g_is_bf16, float* m, float*
  * acc = (init?0:acc) + clamp(g,-clip,clip)*scale ; clip<=0 disables the clamp */
 int b200_clip_accum(const void* g, int g_is_bf16, float* acc, long long n, float clip,
                     float scale, int init, void* stream);
-/* out[b] (+)= sum(x[b,:]^2)   (optimizers/shampoo.py:300-301 Frobenius norms) */
+/* out[b] (+)= sum(x[b,:]^2)   (optimizers/shampoo.py:300-301 Frobenius norms); workspace from
+ * b200_reduce_workspace_bytes(batch) */
 int b200_sumsq(const void* x, int x_is_bf16, float* out, long long numel, int batch,
-               int zero_first, void* stream);
+               int zero_first, void* workspace, size_t workspace_bytes, void* stream);
 /* hi = bf16((src + diag_add*I)*scale), lo = bf16(that - hi) (lo may be NULL); strided [rows,cols] */
 int b200_split_bf16(const float* src, long long ld_src, void* hi, void* lo, long long ld_dst,
                     int rows, int cols, float scale, float diag_add, void* stream);
@@ -120,6 +126,40 @@ int b200_ema_split(const void* g, int g_is_bf16, float* m, float* out32, void* h
 /* p[b] = p[b]*decay + coef[b]*pre[b] + coef_d[b]*d[b] ; p16 = bf16(p) (grafting + decoupled wd) */
 int b200_graft_update(float* p32, void* p16, const float* pre, const float* d, long long numel,
                       int batch, const float* coef, const float* coef_d, float decay, void* stream);
+
+/* ---- Shampoo's Kronecker-factor path (optimizers/shampoo.py), batched over same-shape parameters --------
+ * Factor matrices (statistics L/R, preconditioners P) are f32 [batch, kp, kp], kp = round_up(k, 8), zero
+ * padded; their bf16 hi/lo splits have the same layout.  fp32 operands enter the tensor cores as bf16 hi+lo
+ * pairs (three accumulating GEMMs); a NULL lo pointer means "plain bf16 operand".
+ *
+ * b200_shampoo_stats -- Shampoo._update_statistics (shampoo.py:229-255):
+ *   L = beta2*L + weight * G[:k1,:k2] G[:k1,:k2]^T ;  R = beta2*R + weight * G[:k1,:k2]^T G[:k1,:k2]
+ *   g_hi (/g_lo): bf16 [batch][rows >= k1][ldg >= k2] (the parameter-shaped gradient, read in place);
+ *   weight = (1-beta2) * gscale^2 when the stored gradient still carries a 1/gscale factor. */
+int b200_shampoo_stats(const void* g_hi, const void* g_lo, long long ldg, long long strideG, float* L,
+                       float* R, int batch, int k1, int k2, float beta2, float weight, void* stream);
+/* b200_shampoo_root -- MatrixSqrt.matrix_inverse_pth_root (shampoo.py:88-126), reproduced literally:
+ *   Mt = M + eps*I ; Z = Mt/tr(Mt) ; iters x { Z = Z @ (I + Z/p) } ; P = Z * tr(Mt)^(-1/p^2)
+ *   M, P: f32 [batch,kp,kp] (distinct); P_hi/P_lo (nullable): bf16 split of P for b200_shampoo_precond. */
+size_t b200_shampoo_root_workspace_bytes(int batch, int k);
+int b200_shampoo_root(const float* M, float* P, void* P_hi, void* P_lo, int batch, int k, float p,
+                      float eps, int iters, void* workspace, size_t workspace_bytes, void* stream);
+/* b200_shampoo_precond -- Shampoo._apply_preconditioners (shampoo.py:257-295):
+ *   out[:k1,:k2] = alpha * PL @ m[:k1,:k2] @ PR   (elements of `out` outside the block are left alone)
+ *   m_hi/m_lo: bf16 split of the (bias-corrected) momentum, [batch][rows][ldm]; out: f32 [batch][rows][ldo];
+ *   k2 % 8 == 0, k1 arbitrary. */
+size_t b200_shampoo_precond_workspace_bytes(int batch, int k1, int k2);
+int b200_shampoo_precond(const void* PL_hi, const void* PL_lo, const void* PR_hi, const void* PR_lo,
+                         const void* m_hi, const void* m_lo, long long ldm, long long strideM, float* out,
+                         long long ldo, long long strideO, int batch, int k1, int k2, float alpha,
+                         void* workspace, size_t workspace_bytes, void* stream);
+/* b200_shampoo_graft -- Shampoo._apply_grafting + the parameter write (shampoo.py:297-312,365-373):
+ *   sn = ||upd_b||_F, gn = ||graft_b||_F (f32, overflow to inf like mx.linalg.norm);
+ *   step = sn==0 ? graft : (gn==0 ? upd : upd*gn/sn) ;  p = p*decay + step ; p16 = bf16(p) if non-NULL.
+ *   upd, graft, p32: f32 [batch, numel]. Deterministic reductions. */
+size_t b200_shampoo_graft_workspace_bytes(int batch);
+int b200_shampoo_graft(float* p32, void* p16, const float* upd, const float* graft, long long numel,
+                       int batch, float decay, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- RMSNorm (arch/llama.py:50-56) and RoPE (arch/llama_standard.py:74-75,117-127) ------------ */
 int b200_rmsnorm_fwd(const void* x, const void* w, void* y, float* rstd, int rows, int H,

@@ -26,14 +26,23 @@ SIGNATURES = {
     "b200_newton_schulz_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "b200_newton_schulz": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _f, _f, _vp, _vp, _vp, _sz, _vp]),
     "b200_newton_schulz_allgather": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _f, _f, _vp, _vp, _vp, _sz, _vp, _i, _vp]),
-    "b200_muon_momentum": (_i, [_vp, _i, _vp, _vp, _vp, _ll, _i, _f, _i, _f, _vp]),
+    "b200_reduce_workspace_bytes": (_sz, [_i]),
+    "b200_muon_momentum": (_i, [_vp, _i, _vp, _vp, _vp, _ll, _i, _f, _i, _f, _vp, _sz, _vp]),
+    "b200_shampoo_stats": (_i, [_vp, _vp, _ll, _ll, _vp, _vp, _i, _i, _i, _f, _f, _vp]),
+    "b200_shampoo_root_workspace_bytes": (_sz, [_i, _i]),
+    "b200_shampoo_root": (_i, [_vp, _vp, _vp, _vp, _i, _i, _f, _f, _i, _vp, _sz, _vp]),
+    "b200_shampoo_precond_workspace_bytes": (_sz, [_i, _i, _i]),
+    "b200_shampoo_precond": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _ll, _ll, _vp, _ll, _ll, _i, _i, _i, _f, _vp,
+                                  _sz, _vp]),
+    "b200_shampoo_graft_workspace_bytes": (_sz, [_i]),
+    "b200_shampoo_graft": (_i, [_vp, _vp, _vp, _vp, _ll, _i, _f, _vp, _sz, _vp]),
     "b200_ns_scales": (_i, [_vp, _vp, _vp, _i, _f, _vp]),
     "b200_axpy_update": (_i, [_vp, _vp, _vp, _i, _ll, _f, _vp]),
     "b200_sgd_momentum": (_i, [_vp, _vp, _vp, _i, _vp, _ll, _f, _i, _f, _f, _vp]),
     "b200_adamw": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _ll, _f, _f, _f, _f, _f, _f, _f, _f, _vp]),
     "b200_adam_direction": (_i, [_vp, _vp, _i, _vp, _vp, _ll, _f, _f, _f, _f, _f, _f, _f, _vp]),
     "b200_clip_accum": (_i, [_vp, _i, _vp, _ll, _f, _f, _i, _vp]),
-    "b200_sumsq": (_i, [_vp, _i, _vp, _ll, _i, _i, _vp]),
+    "b200_sumsq": (_i, [_vp, _i, _vp, _ll, _i, _i, _vp, _sz, _vp]),
     "b200_split_bf16": (_i, [_vp, _ll, _vp, _vp, _ll, _i, _i, _f, _f, _vp]),
     "b200_ema_split": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _ll, _f, _f, _f, _f, _vp]),
     "b200_graft_update": (_i, [_vp, _vp, _vp, _vp, _ll, _i, _vp, _vp, _f, _vp]),

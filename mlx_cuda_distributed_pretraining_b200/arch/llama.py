@@ -161,41 +161,37 @@ class Model(nn.Module):
             return self.norm(h)
         return ops.add_rmsnorm(h, pending, self.norm.weight, self.norm.eps)[1]
 
-    def padded_logits(self, inputs: torch.Tensor):
-        """(logits [B*S, ld], V) with ld >= V, ld % 8 == 0 when the fused cross-entropy can take them
-        (tied + row-padded embedding alias, or an aligned vocabulary); else (None, V)."""
-        if self.logit_scale is not None:
-            return None, self.vocab_size
-        h = self.hidden_states(inputs)
+    def _logits_weight(self) -> torch.Tensor:
+        """[V or V_pad, hidden] weight of the logits GEMM: lm_head, or the embedding (tied,
+        arch/llama.py:401-403) through its zero-row-padded alias when V is not a multiple of 8 (with N = 32003
+        cuBLAS falls off its fast path; same values, same gradients, padded classes dropped afterwards)."""
+        if self.lm_head is not None:
+            return self.lm_head.weight
         store = getattr(self, "_b200_store", None)
-        if self.lm_head is None and store is not None and self._tied_w is None:
+        if store is not None and self._tied_w is None:
             w = store.tied_logits_weight()
             self._tied_w = w if w is not None else False
-        if self.lm_head is not None:
-            w = self.lm_head.weight
-        elif self._tied_w is not None and self._tied_w is not False:
-            w = self._tied_w
-        else:
-            w = self.embed_tokens.weight
-        if w.shape[0] % 8 != 0 or h.dtype != torch.bfloat16:
+        if self._tied_w is not None and self._tied_w is not False:
+            return self._tied_w
+        return self.embed_tokens.weight
+
+    def padded_logits(self, inputs: torch.Tensor):
+        """(logits [B*S, ld], V) with ld >= V, ld % 8 == 0 when the fused cross-entropy can take them
+        (bf16 weights, tied + row-padded embedding alias or an aligned vocabulary); else (None, V).
+        Eligibility is decided BEFORE the forward pass, so an ineligible config (fp32, logit_scale,
+        unaligned untied vocabulary) never pays for hidden states it then throws away."""
+        if self.logit_scale is not None:
             return None, self.vocab_size
+        w = self._logits_weight()
+        if w.shape[0] % 8 != 0 or w.dtype != torch.bfloat16:
+            return None, self.vocab_size
+        h = self.hidden_states(inputs)
         logits = torch.nn.functional.linear(h, w)
         return logits.view(-1, logits.shape[-1]), self.vocab_size
 
     def forward(self, inputs: torch.Tensor, position_ids=None, attention_mask=None) -> torch.Tensor:
         h = self.hidden_states(inputs, position_ids, attention_mask)
-        if self.lm_head is None:
-            store = getattr(self, "_b200_store", None)
-            if store is not None and self._tied_w is None:
-                self._tied_w = store.tied_logits_weight() if store.tied_logits_weight() is not None else False
-            if self._tied_w is not None and self._tied_w is not False:
-                # V = 32003 is not a multiple of 8: run the GEMM on the zero-row-padded alias of E
-                # (aligned N), then drop the padded classes.  Same values, same gradients.
-                logits = torch.nn.functional.linear(h, self._tied_w)[..., :self.vocab_size]
-            else:
-                logits = torch.nn.functional.linear(h, self.embed_tokens.weight)
-        else:
-            logits = self.lm_head(h)
+        logits = torch.nn.functional.linear(h, self._logits_weight())[..., :self.vocab_size]
         if self.logit_scale is not None:
             logits = logits * self.logit_scale
         return logits

@@ -442,6 +442,31 @@ class BatchPrefetcher:
         self._thread.join(timeout=5)
 
 
+class EarlyStoppingMonitor:
+    """core/training.py:621-668: stop after `patience` validations without a `min_delta` improvement."""
+
+    def __init__(self, config: Optional[Dict[str, Any]]):
+        config = config or {}
+        self.enabled = config.get("enabled", False)
+        self.patience = config.get("patience", 3)
+        self.min_delta = config.get("min_delta", 0.001)
+        self.metric = config.get("metric", "val_loss")
+        self.mode = config.get("mode", "min")
+        self.best_value = float("inf") if self.mode == "min" else float("-inf")
+        self.counter = 0
+
+    def update(self, metrics: Dict[str, float]) -> bool:
+        if not self.enabled or self.metric not in metrics:
+            return False
+        cur = metrics[self.metric]
+        improved = (self.best_value - cur > self.min_delta) if self.mode == "min" else (cur - self.best_value > self.min_delta)
+        if improved:
+            self.best_value, self.counter = cur, 0
+            return False
+        self.counter += 1
+        return self.counter >= self.patience
+
+
 class Trainer:
     def __init__(self, config, for_training: bool = True, synthetic: Optional[bool] = None,
                  run_root: str = "runs", quiet: bool = False, init_params: Optional[Dict[str, torch.Tensor]] = None):
@@ -548,6 +573,7 @@ class Trainer:
             self.optimizer.shard_ns = bool(self.distributed and self.world > 1 and
                                            os.environ.get("B200_SHARD_NS", "1") != "0")
         self.validation_steps = self.config.logging.steps.get("validation_interval", 0)
+        self.early_stopping = EarlyStoppingMonitor(self.config.training.early_stopping)
         self._pin = None
 
     # -- loss --------------------------------------------------------------------------------------
@@ -568,11 +594,25 @@ class Trainer:
         return (ce * pad_mask).sum() / ntoks, ntoks
 
     def _to_device(self, batch: torch.Tensor) -> torch.Tensor:
-        """Per-step host->device copy of the token batch from pinned memory."""
-        if self._pin is None or self._pin.shape != batch.shape:
-            self._pin = torch.empty(batch.shape, dtype=batch.dtype, pin_memory=True)
-        self._pin.copy_(batch)
-        return self._pin.to(self.device, non_blocking=True)
+        """Per-step host->device copy of the token batch from pinned memory.  The CPU can run a whole step
+        ahead of the GPU, so a staging buffer is only rewritten after the asynchronous copy that last read it
+        has completed (event recorded right after that copy): two rotating buffers, the same guard as
+        BatchPrefetcher.release."""
+        if self._pin is None:
+            self._pin = [[None, None], [None, None]]   # [buffer, event of the last H2D copy that read it]
+            self._pin_next = 0
+        slot = self._pin[self._pin_next]
+        self._pin_next ^= 1
+        if slot[1] is not None:
+            slot[1].synchronize()
+        if slot[0] is None or slot[0].shape != batch.shape or slot[0].dtype != batch.dtype:
+            slot[0] = torch.empty(batch.shape, dtype=batch.dtype, pin_memory=True)
+        slot[0].copy_(batch)
+        dev_batch = slot[0].to(self.device, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        slot[1] = ev
+        return dev_batch
 
     # -- one micro-step + (maybe) update; the unit bench.py times ----------------------------------
     def train_step(self, step: int, batch: Optional[torch.Tensor] = None):
@@ -658,16 +698,22 @@ class Trainer:
         return last
 
     def _train_loop(self, start_step, total_tokens, log_every, ckpt_every, logf, start_time, val_loss, last):
+        pending: Dict[str, Any] = {}   # metrics_to_log of the reference: kept until the next logging step
         for step in range(start_step, self.total_steps):
             loss, ntoks, did_update = self.train_step(step)
             if did_update:
                 total_tokens += self._accum_tokens
                 self._accum_tokens = 0
-            metrics: Dict[str, Any] = {}
             if self.validation_steps > 0 and self.data_manager.has_validation_data and (step + 1) % self.validation_steps == 0:
                 val_loss = self.validate()
                 self.validation_losses.append((step + 1, val_loss))
-                metrics.update(val_loss=val_loss, val_ppl=float(np.exp(val_loss)))
+                pending.update(val_loss=val_loss, val_ppl=float(np.exp(val_loss)))
+                if self.early_stopping.update({"val_loss": val_loss}):   # core/training.py:1726
+                    self.logger.info("Early stopping triggered, ending training")
+                    if logf:
+                        logf.write(f"Step {step}: val_loss={val_loss} | early_stopping=1\n")
+                    break
+            metrics: Dict[str, Any] = {}
             if step % log_every == 0:
                 if self.distributed:  # token-weighted loss across ranks (hybrid_distributed.py:504,519-520)
                     v = torch.stack([loss.float() * ntoks, ntoks.float()])
@@ -676,9 +722,10 @@ class Trainer:
                 else:
                     loss_val, ntok_val = float(loss.item()), int(ntoks.item())
                 tt = int(total_tokens.item()) * (self.world if self.distributed else 1)
-                metrics = {"loss": loss_val, "ppl": float(np.exp(min(loss_val, 80.0))),
+                metrics = {**pending, "loss": loss_val, "ppl": float(np.exp(min(loss_val, 80.0))),
                            "lr": float(self.lr_schedule(step)), "tokens": ntok_val, "total_tokens": tt,
-                           "tokens_per_sec": float(tt / max(time.time() - start_time, 1e-9)), **metrics}
+                           "tokens_per_sec": float(tt / max(time.time() - start_time, 1e-9))}
+                pending = {}
                 last = metrics
                 if logf:
                     line = f"Step {step}: " + " | ".join(f"{k}={v}" for k, v in metrics.items())
@@ -728,18 +775,24 @@ class Trainer:
                     self.store.view(self.store.master, n).copy_(t.to(self.device))
             self.store.refresh_shadow()
         if not reset_optimizer and os.path.exists(f"{checkpoint_path}_optimizer.safetensors"):
-            self.optimizer.init(self.model) if hasattr(self.optimizer, "init") else None
+            self.optimizer.init(self.model)   # allocate state so the saved tensors have somewhere to go
             st = load_file(f"{checkpoint_path}_optimizer.safetensors")
             own = self.optimizer.state_dict()
             with torch.no_grad():
                 for n, t in st.items():
                     if n == "count":
                         self.optimizer.count = int(t.item())
-                    elif n in own:
+                    elif n in own and own[n].is_cuda:
                         own[n].copy_(t.to(self.device))
+            if hasattr(self.optimizer, "load_extra_state"):   # e.g. the hybrid optimizer's AdamW step counter
+                self.optimizer.load_extra_state(st)
+            if hasattr(self.optimizer, "after_load"):         # e.g. Shampoo: rebuild bf16 preconditioner operands
+                self.optimizer.after_load()
         state = json.loads(Path(f"{checkpoint_path}_state.json").read_text())
         self.total_tokens = state.get("total_tokens", 0)
         self.validation_losses = [tuple(x) for x in state.get("validation_losses", [])]
+        if getattr(self, "data_manager", None) is not None:
+            self.data_manager.val_ptr = state.get("val_ptr", 0)   # core/training.py:1469
         return int(state["step"])
 
 

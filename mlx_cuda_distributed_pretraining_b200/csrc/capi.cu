@@ -13,9 +13,22 @@ size_t newton_schulz_workspace_bytes(int batch, int rows, int cols, int steps);
 int newton_schulz(const void* x_in, void* x_out, int batch, int rows, int cols, int steps, float a,
                   float b, float c, const float* inv_norm, const float* inv_norm_sq, void* ws,
                   size_t ws_bytes, const void* const* peer_out, int n_peers, cudaStream_t stream);
+size_t reduce_workspace_bytes(int batch);
 int muon_momentum(const void* g, int g_is_bf16, float* buf, void* u_bf16, float* sumsq,
-                  long long numel, int batch, float mu, int nesterov, float gscale,
-                  cudaStream_t stream);
+                  long long numel, int batch, float mu, int nesterov, float gscale, void* ws,
+                  size_t ws_bytes, cudaStream_t stream);
+int shampoo_stats(const void* g_hi, const void* g_lo, long long ldg, long long strideG, float* L, float* R,
+                  int batch, int k1, int k2, float beta2, float weight, cudaStream_t stream);
+size_t shampoo_root_workspace_bytes(int batch, int k);
+int shampoo_root(const float* M, float* P, void* P_hi, void* P_lo, int batch, int k, float p, float eps, int iters,
+                 void* ws, size_t ws_bytes, cudaStream_t stream);
+size_t shampoo_precond_workspace_bytes(int batch, int k1, int k2);
+int shampoo_precond(const void* PL_hi, const void* PL_lo, const void* PR_hi, const void* PR_lo, const void* m_hi,
+                    const void* m_lo, long long ldm, long long strideM, float* out, long long ldo, long long strideO,
+                    int batch, int k1, int k2, float alpha, void* ws, size_t ws_bytes, cudaStream_t stream);
+size_t shampoo_graft_workspace_bytes(int batch);
+int shampoo_graft(float* p32, void* p16, const float* upd, const float* graft, long long numel, int batch,
+                  float decay, void* ws, size_t ws_bytes, cudaStream_t stream);
 int ns_scales(const float* sumsq, float* inv_norm, float* inv_norm_sq, int batch, float eps,
               cudaStream_t stream);
 int axpy_update(float* p32, void* p16, const void* x, int x_is_bf16, long long n, float s,
@@ -31,7 +44,7 @@ int adam_direction(float* d, const void* g, int g_is_bf16, float* m, float* v, l
 int clip_accum(const void* g, int g_is_bf16, float* acc, long long n, float clip, float scale,
                int init, cudaStream_t stream);
 int sumsq(const void* x, int x_is_bf16, float* out, long long numel, int batch, int zero_first,
-          cudaStream_t stream);
+          void* ws, size_t ws_bytes, cudaStream_t stream);
 int split_bf16(const float* src, long long ld_src, void* hi, void* lo, long long ld_dst, int rows,
                int cols, float scale, float diag_add, cudaStream_t stream);
 int ema_split(const void* g, int g_is_bf16, float* m, float* out32, void* hi, void* lo, long long n,
@@ -69,7 +82,7 @@ int attn_bwd(const void* q, const void* k, const void* v, const void* o, const v
 
 extern "C" {
 
-int b200_version(void) { return 1; }
+int b200_version(void) { return 2; }
 const char* b200_last_error(void) { return b200::last_error(); }
 
 unsigned long long b200_launch_count(void) { return b200::launch_count(); }
@@ -107,11 +120,36 @@ int b200_newton_schulz_allgather(const void* x_in, void* x_out, int batch, int r
   return b200::newton_schulz(x_in, x_out, batch, rows, cols, steps, a, b, c, inv_norm, inv_norm_sq,
                              workspace, workspace_bytes, peer_out, n_peers, S_(stream));
 }
+size_t b200_reduce_workspace_bytes(int batch) { return b200::reduce_workspace_bytes(batch); }
 int b200_muon_momentum(const void* g, int g_is_bf16, float* buf, void* u_bf16, float* sumsq,
                        long long numel, int batch, float mu, int nesterov, float gscale,
-                       void* stream) {
+                       void* workspace, size_t workspace_bytes, void* stream) {
   return b200::muon_momentum(g, g_is_bf16, buf, u_bf16, sumsq, numel, batch, mu, nesterov, gscale,
-                             S_(stream));
+                             workspace, workspace_bytes, S_(stream));
+}
+int b200_shampoo_stats(const void* g_hi, const void* g_lo, long long ldg, long long strideG, float* L,
+                       float* R, int batch, int k1, int k2, float beta2, float weight, void* stream) {
+  return b200::shampoo_stats(g_hi, g_lo, ldg, strideG, L, R, batch, k1, k2, beta2, weight, S_(stream));
+}
+size_t b200_shampoo_root_workspace_bytes(int batch, int k) { return b200::shampoo_root_workspace_bytes(batch, k); }
+int b200_shampoo_root(const float* M, float* P, void* P_hi, void* P_lo, int batch, int k, float p,
+                      float eps, int iters, void* workspace, size_t workspace_bytes, void* stream) {
+  return b200::shampoo_root(M, P, P_hi, P_lo, batch, k, p, eps, iters, workspace, workspace_bytes, S_(stream));
+}
+size_t b200_shampoo_precond_workspace_bytes(int batch, int k1, int k2) {
+  return b200::shampoo_precond_workspace_bytes(batch, k1, k2);
+}
+int b200_shampoo_precond(const void* PL_hi, const void* PL_lo, const void* PR_hi, const void* PR_lo,
+                         const void* m_hi, const void* m_lo, long long ldm, long long strideM, float* out,
+                         long long ldo, long long strideO, int batch, int k1, int k2, float alpha,
+                         void* workspace, size_t workspace_bytes, void* stream) {
+  return b200::shampoo_precond(PL_hi, PL_lo, PR_hi, PR_lo, m_hi, m_lo, ldm, strideM, out, ldo, strideO, batch, k1,
+                               k2, alpha, workspace, workspace_bytes, S_(stream));
+}
+size_t b200_shampoo_graft_workspace_bytes(int batch) { return b200::shampoo_graft_workspace_bytes(batch); }
+int b200_shampoo_graft(float* p32, void* p16, const float* upd, const float* graft, long long numel,
+                       int batch, float decay, void* workspace, size_t workspace_bytes, void* stream) {
+  return b200::shampoo_graft(p32, p16, upd, graft, numel, batch, decay, workspace, workspace_bytes, S_(stream));
 }
 int b200_ns_scales(const float* sumsq, float* inv_norm, float* inv_norm_sq, int batch, float eps,
                    void* stream) {
@@ -142,8 +180,8 @@ int b200_clip_accum(const void* g, int g_is_bf16, float* acc, long long n, float
   return b200::clip_accum(g, g_is_bf16, acc, n, clip, scale, init, S_(stream));
 }
 int b200_sumsq(const void* x, int x_is_bf16, float* out, long long numel, int batch,
-               int zero_first, void* stream) {
-  return b200::sumsq(x, x_is_bf16, out, numel, batch, zero_first, S_(stream));
+               int zero_first, void* workspace, size_t workspace_bytes, void* stream) {
+  return b200::sumsq(x, x_is_bf16, out, numel, batch, zero_first, workspace, workspace_bytes, S_(stream));
 }
 int b200_split_bf16(const float* src, long long ld_src, void* hi, void* lo, long long ld_dst,
                     int rows, int cols, float scale, float diag_add, void* stream) {

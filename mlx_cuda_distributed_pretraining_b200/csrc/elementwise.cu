@@ -63,13 +63,40 @@ __device__ __forceinline__ float block_sum(float v) {
   return t;  // valid in warp 0
 }
 
+// Deterministic grid reduction (no float atomics: data-parallel replicas must compute bit-identical norms,
+// or their fp32 masters drift apart).  Every block parks its partial in `partials[batch][gridDim.x]`; the
+// block that arrives last at the per-matrix counter sums the partials in a fixed order and owns out[b].
+// `tot` must be valid in thread 0.  Counters are zeroed by the host wrapper before the launch.
+__device__ __forceinline__ void grid_reduce_finish(float tot, float* __restrict__ partials,
+                                                   unsigned* __restrict__ counters, float* __restrict__ out,
+                                                   int accumulate) {
+  __shared__ bool is_last;
+  const int b = blockIdx.y;
+  if (threadIdx.x == 0) {
+    partials[(long long)b * gridDim.x + blockIdx.x] = tot;
+    __threadfence();
+    is_last = atomicAdd(counters + b, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  float s = 0.f;
+  for (unsigned i = threadIdx.x; i < gridDim.x; i += EW_THREADS)
+    s += *reinterpret_cast<volatile float*>(partials + (long long)b * gridDim.x + i);
+  s = block_sum(s);
+  if (threadIdx.x == 0) {
+    out[b] = accumulate ? out[b] + s : s;
+    counters[b] = 0;
+  }
+}
+
 // grid = (blocks_per_matrix, batch); every block stays inside one matrix so the Frobenius partial
 // sum goes to a single accumulator.
 template <typename G>
 __global__ void __launch_bounds__(EW_THREADS)
 muon_momentum_kernel(const G* __restrict__ g, float* __restrict__ buf, __nv_bfloat16* __restrict__ u,
                      float* __restrict__ sumsq, long long numel, float mu, int nesterov,
-                     float gscale) {
+                     float gscale, float* __restrict__ partials, unsigned* __restrict__ counters) {
   const long long base = (long long)blockIdx.y * numel;
   const G* gp = g + base;
   float* bp = buf + base;
@@ -104,7 +131,7 @@ muon_momentum_kernel(const G* __restrict__ g, float* __restrict__ buf, __nv_bflo
     }
   }
   const float tot = block_sum(ss);
-  if (threadIdx.x == 0) atomicAdd(sumsq + blockIdx.y, tot);
+  grid_reduce_finish(tot, partials, counters, sumsq, 0);
 }
 
 __global__ void ns_scales_kernel(const float* __restrict__ sumsq, float* __restrict__ inv_norm,
@@ -148,15 +175,33 @@ sgd_momentum_kernel(float* __restrict__ p32, __nv_bfloat16* __restrict__ p16,
                     const G* __restrict__ g, float* __restrict__ buf, long long n, float mu,
                     int nesterov, float lr, float gscale) {
   const float omm = 1.0f - mu;
-  for (long long i = (long long)blockIdx.x * EW_THREADS + threadIdx.x; i < n;
+  const long long nvec = n / 8;
+  for (long long i = (long long)blockIdx.x * EW_THREADS + threadIdx.x; i < nvec;
        i += (long long)gridDim.x * EW_THREADS) {
-    const float gj = ldf(g + i) * gscale;
-    const float b = omm * gj + mu * buf[i];
-    const float uu = nesterov ? gj + mu * b : b;
-    buf[i] = b;
-    const float v = p32[i] - lr * uu;
-    p32[i] = v;
-    if (p16) p16[i] = __float2bfloat16_rn(v);
+    float gv[8], bv[8], pv[8];
+    load8(g + i * 8, gv);
+    load8(buf + i * 8, bv);
+    load8(p32 + i * 8, pv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float gj = gv[j] * gscale;
+      bv[j] = omm * gj + mu * bv[j];
+      pv[j] -= lr * (nesterov ? gj + mu * bv[j] : bv[j]);
+    }
+    store8(buf + i * 8, bv);
+    store8(p32 + i * 8, pv);
+    if (p16) store8(p16 + i * 8, pv);
+  }
+  if (blockIdx.x == 0) {
+    for (long long i = nvec * 8 + threadIdx.x; i < n; i += EW_THREADS) {
+      const float gj = ldf(g + i) * gscale;
+      const float b = omm * gj + mu * buf[i];
+      const float uu = nesterov ? gj + mu * b : b;
+      buf[i] = b;
+      const float v = p32[i] - lr * uu;
+      p32[i] = v;
+      if (p16) p16[i] = __float2bfloat16_rn(v);
+    }
   }
 }
 
@@ -212,14 +257,33 @@ adam_direction_kernel(float* __restrict__ d, const G* __restrict__ g, float* __r
                       float bc1, float bc2, float gscale) {
   const float step = lr / bc1;
   const float rs_bc2 = rsqrtf(bc2);
-  for (long long i = (long long)blockIdx.x * EW_THREADS + threadIdx.x; i < n;
+  const long long nvec = n / 8;
+  for (long long i = (long long)blockIdx.x * EW_THREADS + threadIdx.x; i < nvec;
        i += (long long)gridDim.x * EW_THREADS) {
-    const float gj = ldf(g + i) * gscale;
-    const float mm = b1 * m[i] + (1.0f - b1) * gj;
-    const float vv = b2 * v[i] + (1.0f - b2) * gj * gj;
-    m[i] = mm;
-    v[i] = vv;
-    d[i] = -step * mm / (sqrtf(vv) * rs_bc2 + eps);
+    float gv[8], mv[8], vv[8], dv[8];
+    load8(g + i * 8, gv);
+    load8(m + i * 8, mv);
+    load8(v + i * 8, vv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float gj = gv[j] * gscale;
+      mv[j] = b1 * mv[j] + (1.0f - b1) * gj;
+      vv[j] = b2 * vv[j] + (1.0f - b2) * gj * gj;
+      dv[j] = -step * mv[j] / (sqrtf(vv[j]) * rs_bc2 + eps);
+    }
+    store8(m + i * 8, mv);
+    store8(v + i * 8, vv);
+    store8(d + i * 8, dv);
+  }
+  if (blockIdx.x == 0) {
+    for (long long i = nvec * 8 + threadIdx.x; i < n; i += EW_THREADS) {
+      const float gj = ldf(g + i) * gscale;
+      const float mm = b1 * m[i] + (1.0f - b1) * gj;
+      const float vv = b2 * v[i] + (1.0f - b2) * gj * gj;
+      m[i] = mm;
+      v[i] = vv;
+      d[i] = -step * mm / (sqrtf(vv) * rs_bc2 + eps);
+    }
   }
 }
 
@@ -256,10 +320,11 @@ clip_accum_kernel(const G* __restrict__ g, float* __restrict__ acc, long long n,
   }
 }
 
-// out[b] += sum(x[b, :]^2), grid = (blocks, batch)
+// out[b] (+)= sum(x[b, :]^2), grid = (blocks, batch); deterministic (see grid_reduce_finish)
 template <typename X>
 __global__ void __launch_bounds__(EW_THREADS)
-sumsq_kernel(const X* __restrict__ x, float* __restrict__ out, long long numel) {
+sumsq_kernel(const X* __restrict__ x, float* __restrict__ out, long long numel, int accumulate,
+             float* __restrict__ partials, unsigned* __restrict__ counters) {
   const X* xp = x + (long long)blockIdx.y * numel;
   float ss = 0.f;
   const long long nvec = numel / 8;
@@ -276,7 +341,7 @@ sumsq_kernel(const X* __restrict__ x, float* __restrict__ out, long long numel) 
       ss += t * t;
     }
   const float tot = block_sum(ss);
-  if (threadIdx.x == 0) atomicAdd(out + blockIdx.y, tot);
+  grid_reduce_finish(tot, partials, counters, out, accumulate);
 }
 
 // dst(bf16) = src(fp32) (strided 2-D block copy with cast; used for Shampoo's [:k,:k] sub-blocks
@@ -306,15 +371,35 @@ __global__ void __launch_bounds__(EW_THREADS)
 ema_split_kernel(const G* __restrict__ g, float* __restrict__ m, float* __restrict__ out32,
                  __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, long long n,
                  float beta, float gscale, float inv_bc, float out_scale) {
-  for (long long i = (long long)blockIdx.x * EW_THREADS + threadIdx.x; i < n;
+  const long long nvec = n / 8;
+  for (long long i = (long long)blockIdx.x * EW_THREADS + threadIdx.x; i < nvec;
        i += (long long)gridDim.x * EW_THREADS) {
-    const float mm = beta * m[i] + (1.0f - beta) * ldf(g + i) * gscale;
-    m[i] = mm;
-    const float mh = mm * inv_bc;
-    out32[i] = mh * out_scale;
-    const __nv_bfloat16 h = __float2bfloat16_rn(mh);
-    hi[i] = h;
-    if (lo) lo[i] = __float2bfloat16_rn(mh - __bfloat162float(h));
+    float gv[8], mv[8], ov[8], hv[8], lv[8];
+    load8(g + i * 8, gv);
+    load8(m + i * 8, mv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      mv[j] = beta * mv[j] + (1.0f - beta) * gv[j] * gscale;
+      const float mh = mv[j] * inv_bc;
+      ov[j] = mh * out_scale;
+      hv[j] = __bfloat162float(__float2bfloat16_rn(mh));
+      lv[j] = mh - hv[j];
+    }
+    store8(m + i * 8, mv);
+    store8(out32 + i * 8, ov);
+    store8(hi + i * 8, hv);
+    if (lo) store8(lo + i * 8, lv);
+  }
+  if (blockIdx.x == 0) {
+    for (long long i = nvec * 8 + threadIdx.x; i < n; i += EW_THREADS) {
+      const float mm = beta * m[i] + (1.0f - beta) * ldf(g + i) * gscale;
+      m[i] = mm;
+      const float mh = mm * inv_bc;
+      out32[i] = mh * out_scale;
+      const __nv_bfloat16 h = __float2bfloat16_rn(mh);
+      hi[i] = h;
+      if (lo) lo[i] = __float2bfloat16_rn(mh - __bfloat162float(h));
+    }
   }
 }
 
@@ -326,11 +411,33 @@ graft_update_kernel(float* __restrict__ p32, __nv_bfloat16* __restrict__ p16,
                     const float* __restrict__ coef, const float* __restrict__ coef_d, float decay) {
   const long long base = (long long)blockIdx.y * numel;
   const float c = coef[blockIdx.y], cd = coef_d[blockIdx.y];
-  for (long long i = (long long)blockIdx.x * EW_THREADS + threadIdx.x; i < numel;
+  // batched use has numel % 8 == 0 (checked by the host wrapper), so `base` keeps 16-byte alignment
+  const long long nvec = numel / 8;
+  for (long long i = (long long)blockIdx.x * EW_THREADS + threadIdx.x; i < nvec;
        i += (long long)gridDim.x * EW_THREADS) {
-    const float v = p32[base + i] * decay + c * pre[base + i] + cd * d[base + i];
-    p32[base + i] = v;
-    if (p16) p16[base + i] = __float2bfloat16_rn(v);
+    float pv[8], rv[8], dv[8];
+    load8(p32 + base + i * 8, pv);
+    load8(pre + base + i * 8, rv);
+    load8(d + base + i * 8, dv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      // a zero coefficient must drop its term even when the term is inf/nan (overflowed Shampoo step, D10)
+      float v = pv[j] * decay;
+      if (c != 0.f) v += c * rv[j];
+      if (cd != 0.f) v += cd * dv[j];
+      pv[j] = v;
+    }
+    store8(p32 + base + i * 8, pv);
+    if (p16) store8(p16 + base + i * 8, pv);
+  }
+  if (blockIdx.x == 0) {
+    for (long long i = nvec * 8 + threadIdx.x; i < numel; i += EW_THREADS) {
+      float v = p32[base + i] * decay;
+      if (c != 0.f) v += c * pre[base + i];
+      if (cd != 0.f) v += cd * d[base + i];
+      p32[base + i] = v;
+      if (p16) p16[base + i] = __float2bfloat16_rn(v);
+    }
   }
 }
 
@@ -346,9 +453,31 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 
 }  // namespace
 
+// Scratch of the deterministic grid reductions: one partial per block (at most 8 blocks per SM over the
+// whole batch, plus one per matrix) and one arrival counter per matrix.
+size_t reduce_workspace_bytes(int batch) {
+  if (batch < 1) batch = 1;
+  return (((size_t)num_sms() * 8 + 2 * (size_t)batch) * 4 + 255) & ~size_t(255);
+}
+
+// splits a caller workspace into (partials, counters) and zeroes the counters on `stream`
+static int reduce_ws(void* ws, size_t ws_bytes, int batch, int gx, float** partials, unsigned** counters,
+                     cudaStream_t stream) {
+  if (ws == nullptr || ws_bytes < reduce_workspace_bytes(batch) ||
+      (size_t)gx * batch + batch > reduce_workspace_bytes(batch) / 4) {
+    set_error("reduction workspace too small (%zu < %zu bytes for batch %d)", ws_bytes,
+              reduce_workspace_bytes(batch), batch);
+    return B200_ERR_WORKSPACE;
+  }
+  *counters = reinterpret_cast<unsigned*>(ws);
+  *partials = reinterpret_cast<float*>(ws) + batch;
+  B200_CHECK_CUDA(cudaMemsetAsync(*counters, 0, sizeof(unsigned) * batch, stream));
+  return B200_OK;
+}
+
 int muon_momentum(const void* g, int g_is_bf16, float* buf, void* u_bf16, float* sumsq,
-                  long long numel, int batch, float mu, int nesterov, float gscale,
-                  cudaStream_t stream) {
+                  long long numel, int batch, float mu, int nesterov, float gscale, void* ws,
+                  size_t ws_bytes, cudaStream_t stream) {
   B200_CHECK_ARG(numel > 0 && batch > 0, "muon_momentum: empty");
   B200_CHECK_ARG(aligned16(g) && aligned16(buf) && aligned16(u_bf16),
                  "muon_momentum: buffers must be 16-byte aligned");
@@ -359,13 +488,16 @@ int muon_momentum(const void* g, int g_is_bf16, float* buf, void* u_bf16, float*
   const int cap = (num_sms() * 8 + batch - 1) / batch;
   if (gx > cap) gx = cap < 1 ? 1 : cap;
   dim3 grid(gx, batch);
-  B200_CHECK_CUDA(cudaMemsetAsync(sumsq, 0, sizeof(float) * batch, stream));
+  float* partials;
+  unsigned* counters;
+  if (int rc = reduce_ws(ws, ws_bytes, batch, gx, &partials, &counters, stream)) return rc;
   if (g_is_bf16)
     muon_momentum_kernel<__nv_bfloat16><<<grid, EW_THREADS, 0, stream>>>(
-        (const __nv_bfloat16*)g, buf, (__nv_bfloat16*)u_bf16, sumsq, numel, mu, nesterov, gscale);
+        (const __nv_bfloat16*)g, buf, (__nv_bfloat16*)u_bf16, sumsq, numel, mu, nesterov, gscale, partials,
+        counters);
   else
     muon_momentum_kernel<float><<<grid, EW_THREADS, 0, stream>>>(
-        (const float*)g, buf, (__nv_bfloat16*)u_bf16, sumsq, numel, mu, nesterov, gscale);
+        (const float*)g, buf, (__nv_bfloat16*)u_bf16, sumsq, numel, mu, nesterov, gscale, partials, counters);
   B200_CHECK_LAUNCH();
   return B200_OK;
 }
@@ -397,7 +529,9 @@ int axpy_update(float* p32, void* p16, const void* x, int x_is_bf16, long long n
 int sgd_momentum(float* p32, void* p16, const void* g, int g_is_bf16, float* buf, long long n,
                  float mu, int nesterov, float lr, float gscale, cudaStream_t stream) {
   B200_CHECK_ARG(n > 0, "sgd_momentum: empty");
-  const int grid = ew_grid(n);
+  B200_CHECK_ARG(aligned16(p32) && aligned16(p16) && aligned16(g) && aligned16(buf),
+                 "sgd_momentum: buffers must be 16-byte aligned");
+  const int grid = ew_grid(n / 8 + 1);
   if (g_is_bf16)
     sgd_momentum_kernel<__nv_bfloat16><<<grid, EW_THREADS, 0, stream>>>(
         p32, (__nv_bfloat16*)p16, (const __nv_bfloat16*)g, buf, n, mu, nesterov, lr, gscale);
@@ -431,7 +565,9 @@ int adam_direction(float* d, const void* g, int g_is_bf16, float* m, float* v, l
                    float lr, float b1, float b2, float eps, float bc1, float bc2, float gscale,
                    cudaStream_t stream) {
   B200_CHECK_ARG(n > 0, "adam_direction: empty");
-  const int grid = ew_grid(n);
+  B200_CHECK_ARG(aligned16(d) && aligned16(g) && aligned16(m) && aligned16(v),
+                 "adam_direction: buffers must be 16-byte aligned");
+  const int grid = ew_grid(n / 8 + 1);
   if (g_is_bf16)
     adam_direction_kernel<__nv_bfloat16><<<grid, EW_THREADS, 0, stream>>>(
         d, (const __nv_bfloat16*)g, m, v, n, lr, b1, b2, eps, bc1, bc2, gscale);
@@ -458,18 +594,22 @@ int clip_accum(const void* g, int g_is_bf16, float* acc, long long n, float clip
 }
 
 int sumsq(const void* x, int x_is_bf16, float* out, long long numel, int batch, int zero_first,
-          cudaStream_t stream) {
+          void* ws, size_t ws_bytes, cudaStream_t stream) {
   B200_CHECK_ARG(numel > 0 && batch > 0, "sumsq: empty");
   B200_CHECK_ARG(aligned16(x) && (batch == 1 || numel % 8 == 0), "sumsq: alignment");
   int gx = ew_grid(numel / 8 + 1);
   const int cap = (num_sms() * 8 + batch - 1) / batch;
   if (gx > cap) gx = cap < 1 ? 1 : cap;
-  if (zero_first) B200_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * batch, stream));
   dim3 grid(gx, batch);
+  float* partials;
+  unsigned* counters;
+  if (int rc = reduce_ws(ws, ws_bytes, batch, gx, &partials, &counters, stream)) return rc;
   if (x_is_bf16)
-    sumsq_kernel<__nv_bfloat16><<<grid, EW_THREADS, 0, stream>>>((const __nv_bfloat16*)x, out, numel);
+    sumsq_kernel<__nv_bfloat16><<<grid, EW_THREADS, 0, stream>>>((const __nv_bfloat16*)x, out, numel,
+                                                                zero_first ? 0 : 1, partials, counters);
   else
-    sumsq_kernel<float><<<grid, EW_THREADS, 0, stream>>>((const float*)x, out, numel);
+    sumsq_kernel<float><<<grid, EW_THREADS, 0, stream>>>((const float*)x, out, numel, zero_first ? 0 : 1,
+                                                        partials, counters);
   B200_CHECK_LAUNCH();
   return B200_OK;
 }
@@ -488,7 +628,9 @@ int split_bf16(const float* src, long long ld_src, void* hi, void* lo, long long
 int ema_split(const void* g, int g_is_bf16, float* m, float* out32, void* hi, void* lo, long long n,
               float beta, float gscale, float inv_bc, float out_scale, cudaStream_t stream) {
   B200_CHECK_ARG(n > 0, "ema_split: empty");
-  const int grid = ew_grid(n);
+  B200_CHECK_ARG(aligned16(g) && aligned16(m) && aligned16(out32) && aligned16(hi) && aligned16(lo),
+                 "ema_split: buffers must be 16-byte aligned");
+  const int grid = ew_grid(n / 8 + 1);
   if (g_is_bf16)
     ema_split_kernel<__nv_bfloat16><<<grid, EW_THREADS, 0, stream>>>(
         (const __nv_bfloat16*)g, m, out32, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, n, beta, gscale, inv_bc, out_scale);
@@ -502,7 +644,10 @@ int ema_split(const void* g, int g_is_bf16, float* m, float* out32, void* hi, vo
 int graft_update(float* p32, void* p16, const float* pre, const float* d, long long numel, int batch,
                  const float* coef, const float* coef_d, float decay, cudaStream_t stream) {
   B200_CHECK_ARG(numel > 0 && batch > 0, "graft_update: empty");
-  int gx = ew_grid(numel);
+  B200_CHECK_ARG(aligned16(p32) && aligned16(p16) && aligned16(pre) && aligned16(d) &&
+                     (batch == 1 || numel % 8 == 0),
+                 "graft_update: buffers must be 16-byte aligned (batched: numel %% 8 == 0)");
+  int gx = ew_grid(numel / 8 + 1);
   const int cap = (num_sms() * 8 + batch - 1) / batch;
   if (gx > cap) gx = cap < 1 ? 1 : cap;
   dim3 grid(gx, batch);

@@ -319,10 +319,18 @@ int gemm_bf16(bool a_mn, bool b_mn, int M, int N, int K, int batch, const void* 
               int force_bn, cudaStream_t stream) {
   B200_CHECK_ARG(M > 0 && N > 0 && K > 0 && batch > 0, "gemm: empty problem M=%d N=%d K=%d b=%d", M,
                  N, K, batch);
-  B200_CHECK_ARG(N % 8 == 0, "gemm: N=%d must be a multiple of 8", N);
   B200_CHECK_ARG(lda % 8 == 0 && ldb % 8 == 0, "gemm: lda=%lld ldb=%lld must be multiples of 8", lda,
                  ldb);
   const int out_vec = out_f32 ? 4 : 8;
+  // N need not be a multiple of the store vector as long as the padded row exists: the epilogue writes whole
+  // 16-byte vectors, so columns [N, round_up(N, vec)) of D receive alpha*0 + beta*C (B rows >= N are zero-filled
+  // by TMA).  Used by Shampoo's [259, 259] factor of the byte-level embedding (stored with ld = 264).
+  {
+    const long long n_pad = ((long long)N + out_vec - 1) / out_vec * out_vec;
+    B200_CHECK_ARG(N % out_vec == 0 || (ldd >= n_pad && (C == nullptr || ldc >= n_pad) && force_bn != 1256),
+                   "gemm: N=%d is not a multiple of %d and ldd=%lld/ldc=%lld leave no room for the padded vector",
+                   N, out_vec, ldd, ldc);
+  }
   B200_CHECK_ARG(ldd % out_vec == 0 && (C == nullptr || ldc % out_vec == 0),
                  "gemm: ldd=%lld ldc=%lld must be multiples of %d", ldd, ldc, out_vec);
   B200_CHECK_ARG((reinterpret_cast<uintptr_t>(D) & 15u) == 0 &&

@@ -132,6 +132,20 @@ def ns_workspace_bytes(batch: int, rows: int, cols: int, steps: int) -> int:
     return int(lib().b200_newton_schulz_workspace_bytes(batch, rows, cols, steps))
 
 
+_REDUCE_WS = {}
+
+
+def reduce_workspace(device, batch: int) -> torch.Tensor:
+    """Scratch of the deterministic grid reductions (b200_reduce_workspace_bytes), one per (device, stream)."""
+    key = (str(device), torch.cuda.current_stream().cuda_stream)
+    need = int(lib().b200_reduce_workspace_bytes(int(batch)))
+    ws = _REDUCE_WS.get(key)
+    if ws is None or ws.numel() < need:
+        ws = torch.empty(need, device=device, dtype=torch.uint8)
+        _REDUCE_WS[key] = ws
+    return ws
+
+
 def sumsq(x: torch.Tensor, out: Optional[torch.Tensor] = None, zero_first: bool = True) -> torch.Tensor:
     """Per-matrix sum of squares of x [batch, ...] -> fp32 [batch]."""
     xb = x if x.dim() >= 2 else x.unsqueeze(0)
@@ -139,8 +153,9 @@ def sumsq(x: torch.Tensor, out: Optional[torch.Tensor] = None, zero_first: bool 
     numel = x.numel() // batch
     if out is None:
         out = torch.empty(batch, device=x.device, dtype=torch.float32)
+    ws = reduce_workspace(x.device, batch)
     check(lib().b200_sumsq(x.data_ptr(), _is_bf16(x, "x"), out.data_ptr(), numel, batch,
-                           int(zero_first), _stream()), "b200_sumsq")
+                           int(zero_first), ws.data_ptr(), ws.numel(), _stream()), "b200_sumsq")
     return out
 
 
@@ -194,9 +209,10 @@ def muon_momentum(g: torch.Tensor, buf: torch.Tensor, u: torch.Tensor, sumsq_out
     _need(u, torch.bfloat16, "u")
     batch = g.shape[0] if g.dim() == 3 else 1
     numel = g.numel() // batch
+    ws = reduce_workspace(g.device, batch)
     check(lib().b200_muon_momentum(g.data_ptr(), _is_bf16(g, "g"), buf.data_ptr(), u.data_ptr(),
                                    sumsq_out.data_ptr(), numel, batch, float(mu), int(nesterov),
-                                   float(gscale), _stream()), "b200_muon_momentum")
+                                   float(gscale), ws.data_ptr(), ws.numel(), _stream()), "b200_muon_momentum")
 
 
 def axpy_update(p32: torch.Tensor, p16: Optional[torch.Tensor], x: torch.Tensor, s: float) -> None:
@@ -577,8 +593,63 @@ def graft_update(p32, p16, pre, d, numel: int, batch: int, coef, coef_d, decay: 
 
 
 def sumsq_raw(x: torch.Tensor, out: torch.Tensor, numel: int, batch: int, zero_first: bool = True) -> None:
+    ws = reduce_workspace(x.device, batch)
     check(lib().b200_sumsq(x.data_ptr(), _is_bf16(x, "x"), out.data_ptr(), numel, batch, int(zero_first),
-                           _stream()), "b200_sumsq")
+                           ws.data_ptr(), ws.numel(), _stream()), "b200_sumsq")
+
+
+# ------------------------------------------------------------------------------------------------
+# Shampoo's Kronecker-factor path through the C ABI (b200_shampoo_*); factor matrices are [batch, kp, kp]
+# with kp = round_up(k, 8)
+# ------------------------------------------------------------------------------------------------
+def rup8(k: int) -> int:
+    return (int(k) + 7) // 8 * 8
+
+
+def shampoo_stats(g_hi: torch.Tensor, g_lo: Optional[torch.Tensor], ldg: int, stride_g: int, L: torch.Tensor,
+                  R: torch.Tensor, batch: int, k1: int, k2: int, beta2: float, weight: float) -> None:
+    _need(L, torch.float32, "L")
+    _need(R, torch.float32, "R")
+    check(lib().b200_shampoo_stats(g_hi.data_ptr(), _ptr(g_lo), int(ldg), int(stride_g), L.data_ptr(), R.data_ptr(),
+                                   int(batch), int(k1), int(k2), float(beta2), float(weight), _stream()),
+          "b200_shampoo_stats")
+
+
+def shampoo_root(M: torch.Tensor, P: torch.Tensor, P_hi: Optional[torch.Tensor], P_lo: Optional[torch.Tensor],
+                 k: int, p: float, eps: float, iters: int = 6, workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """matrix_inverse_pth_root (optimizers/shampoo.py:88-126) of M [batch, kp, kp] fp32 -> P (same layout)."""
+    _need(M, torch.float32, "M")
+    _need(P, torch.float32, "P")
+    batch = M.shape[0]
+    need = int(lib().b200_shampoo_root_workspace_bytes(batch, int(k)))
+    if workspace is None or workspace.numel() < need:
+        workspace = torch.empty(need, device=M.device, dtype=torch.uint8)
+    check(lib().b200_shampoo_root(M.data_ptr(), P.data_ptr(), _ptr(P_hi), _ptr(P_lo), batch, int(k), float(p),
+                                  float(eps), int(iters), workspace.data_ptr(), workspace.numel(), _stream()),
+          "b200_shampoo_root")
+    return P
+
+
+def shampoo_precond(PLh, PLl, PRh, PRl, m_hi, m_lo, ldm: int, stride_m: int, out: torch.Tensor, ldo: int,
+                    stride_o: int, batch: int, k1: int, k2: int, alpha: float,
+                    workspace: Optional[torch.Tensor] = None) -> None:
+    need = int(lib().b200_shampoo_precond_workspace_bytes(int(batch), int(k1), int(k2)))
+    if workspace is None or workspace.numel() < need:
+        workspace = torch.empty(need, device=out.device, dtype=torch.uint8)
+    check(lib().b200_shampoo_precond(PLh.data_ptr(), _ptr(PLl), PRh.data_ptr(), _ptr(PRl), m_hi.data_ptr(),
+                                     _ptr(m_lo), int(ldm), int(stride_m), out.data_ptr(), int(ldo), int(stride_o),
+                                     int(batch), int(k1), int(k2), float(alpha), workspace.data_ptr(),
+                                     workspace.numel(), _stream()), "b200_shampoo_precond")
+
+
+def shampoo_graft(p32: torch.Tensor, p16: Optional[torch.Tensor], upd: torch.Tensor, graft: torch.Tensor,
+                  numel: int, batch: int, decay: float, workspace: Optional[torch.Tensor] = None) -> None:
+    need = int(lib().b200_shampoo_graft_workspace_bytes(int(batch)))
+    if workspace is None or workspace.numel() < need:
+        workspace = torch.empty(need, device=p32.device, dtype=torch.uint8)
+    check(lib().b200_shampoo_graft(p32.data_ptr(), _ptr(p16), upd.data_ptr(), graft.data_ptr(), int(numel),
+                                   int(batch), float(decay), workspace.data_ptr(), workspace.numel(), _stream()),
+          "b200_shampoo_graft")
 
 
 # ------------------------------------------------------------------------------------------------

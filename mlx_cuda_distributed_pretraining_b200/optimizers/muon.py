@@ -131,10 +131,12 @@ class Muon:
             buf = self._buf[g.offset:g.offset + n]
             u = self._u[:n]
             x = self._x[:n] if world == 1 else self._xg[gi]
+            rws = ops.reduce_workspace(store.device, g.batch)
             ops.check(lib.b200_muon_momentum(gg.data_ptr(), ops._is_bf16(gg, "grad"), buf.data_ptr(),
                                              u.data_ptr(), self._ss.data_ptr(), rc, g.batch,
                                              float(self.momentum), int(self.nesterov),
-                                             float(self.grad_scale), stream), "b200_muon_momentum")
+                                             float(self.grad_scale), rws.data_ptr(), rws.numel(), stream),
+                      "b200_muon_momentum")
             ops.check(lib.b200_ns_scales(self._ss.data_ptr(), self._inv.data_ptr(), self._inv2.data_ptr(),
                                          g.batch, ops.NS_EPS, stream), "b200_ns_scales")
             mine = self.owned_ranges_of(gi, world, rank)   # matrices this rank orthogonalises
@@ -215,9 +217,11 @@ class Muon:
             buf = self._buf[g.offset:g.offset + n]
             with torch.cuda.stream(st):
                 sp = ops._stream()
+                rws = ops.reduce_workspace(store.device, g.batch)   # keyed by stream: one per side stream
                 ops.check(lib.b200_muon_momentum(gg.data_ptr(), ops._is_bf16(gg, "grad"), buf.data_ptr(), u_.data_ptr(),
                                                  ss_.data_ptr(), rc, g.batch, float(self.momentum), int(self.nesterov),
-                                                 float(self.grad_scale), sp), "b200_muon_momentum")
+                                                 float(self.grad_scale), rws.data_ptr(), rws.numel(), sp),
+                          "b200_muon_momentum")
                 ops.check(lib.b200_ns_scales(ss_.data_ptr(), inv_.data_ptr(), inv2_.data_ptr(), g.batch, ops.NS_EPS, sp),
                           "b200_ns_scales")
                 ops.check(lib.b200_newton_schulz(u_.data_ptr(), x_.data_ptr(), g.batch, g.rows, g.cols, self.ns_steps,

@@ -1,5 +1,5 @@
 """Shampoo with the reference's surface (optimizers/shampoo.py:20-45,143-378) on the sm_100a GEMM
-engine.
+engine, orchestrated through the C ABI's b200_shampoo_* entry points (include/b200_hotpath.h).
 
     opt = Shampoo(learning_rate=float|callable, params=ShampooParams(...))
     opt.update(model, gradients)     # core/training.py:1690,1700
@@ -7,19 +7,25 @@ engine.
 Per step (shampoo.py:314-378, with the wiring defects D1/D2/D9 of SURVEY 2.3 fixed):
   count += 1; lr = sched(count)
   grafting direction d = Adam step (mlx Adam, no bias correction) computed WITHOUT applying it
-  L = b2 L + (1-b2) G G^T ; R = b2 R + (1-b2) G^T G       on G[:1024,:1024]   (:229-255)
-  every `update_period` steps after `start_preconditioning_step`:
+  L = b2 L + (1-b2) G G^T ; R = b2 R + (1-b2) G^T G       on G[:1024,:1024]   (:229-255)  b200_shampoo_stats
+  every `update_period` steps after `start_preconditioning_step`:                          b200_shampoo_root
         P = matrix_inverse_pth_root(stat)  -- the reference's literal formula (:88-126):
         Z0 = (M+eps I)/tr ; 6x Z <- Z + Z Z / p ; P = Z * tr^(-1/p^2)        (not a true inverse root)
   m = b1 m + (1-b1) g ; mhat = m/(1-b1^t) ; pre = mhat with pre[:1024,:1024] = PL mhat PR   (:257-295)
+                                                                                           b200_shampoo_precond
   upd = -lr*pre rescaled to ||d||_F (grafting, :297-312) ; decoupled wd: upd -= lr*wd*p     (:372-373)
+                                                                                           b200_shampoo_graft
 
-All matrix products are batched over the same-shape parameters of a flat.ParamStore group and run
-on tcgen05.  fp32 matrices enter the tensor cores as bf16 hi+lo pairs (hi*hi + hi*lo + lo*hi, three
-accumulating GEMMs, ~16 mantissa bits) so the statistics/roots stay close to the reference's fp32
-matmuls; gradients (already bf16 under mixed precision) are used as they are.
-Parameters whose preconditioned block side is not a multiple of 8 (only the byte-level embedding
-[259, hidden]) are not preconditioned (momentum + grafting only) -- see DESIGN.md.
+All matrix products are batched over the same-shape parameters of a flat.ParamStore group and run on
+tcgen05.  fp32 matrices enter the tensor cores as bf16 hi+lo pairs (hi*hi + hi*lo + lo*hi, three
+accumulating GEMMs, ~16 mantissa bits) so statistics/roots stay close to the reference's fp32 matmuls;
+bf16 gradients (mixed precision) are used as they are, fp32 gradients are split the same way.
+State per parameter mirrors the reference's (:180-208): momentum, statistics.0/1, preconditioners.0/1
+(+ the grafting optimizer's moments), all fp32 and all checkpointed; the bf16 hi/lo copies of the
+preconditioners are derived data, rebuilt by `after_load()`.
+Factor sides that are not multiples of 8 (the byte-level embedding's [259, 259]) are stored zero-padded
+to [264, 264]; only a preconditioned COLUMN count that is not a multiple of 8 disables preconditioning
+for a group (momentum + grafting only) -- impossible with ParamStore's cols % 8 rule and the default cap.
 """
 from __future__ import annotations
 
@@ -60,18 +66,23 @@ class ShampooParams:
 
 
 class _GroupState:
+    """Kronecker factors of one shape group: [batch, kp, kp] fp32 (+ bf16 hi/lo of the preconditioners)."""
+
     def __init__(self, g: MatGroup, cap: int, dev):
         self.k1, self.k2 = min(g.rows, cap), min(g.cols, cap)
-        self.enabled = self.k1 % 8 == 0 and self.k2 % 8 == 0
+        self.k1p, self.k2p = ops.rup8(self.k1), ops.rup8(self.k2)
+        self.enabled = self.k2 % 8 == 0
         if not self.enabled:
             return
         b = g.batch
-        self.L = torch.zeros(b, self.k1, self.k1, dtype=torch.float32, device=dev)
-        self.R = torch.zeros(b, self.k2, self.k2, dtype=torch.float32, device=dev)
-        self.PLh = torch.zeros(b, self.k1, self.k1, dtype=torch.bfloat16, device=dev)
-        self.PLl = torch.zeros_like(self.PLh)
-        self.PRh = torch.zeros(b, self.k2, self.k2, dtype=torch.bfloat16, device=dev)
-        self.PRl = torch.zeros_like(self.PRh)
+        f32 = dict(dtype=torch.float32, device=dev)
+        bf = dict(dtype=torch.bfloat16, device=dev)
+        self.L = torch.zeros(b, self.k1p, self.k1p, **f32)
+        self.R = torch.zeros(b, self.k2p, self.k2p, **f32)
+        self.PL = torch.zeros(b, self.k1p, self.k1p, **f32)
+        self.PR = torch.zeros(b, self.k2p, self.k2p, **f32)
+        self.PLh, self.PLl = torch.zeros(b, self.k1p, self.k1p, **bf), torch.zeros(b, self.k1p, self.k1p, **bf)
+        self.PRh, self.PRl = torch.zeros(b, self.k2p, self.k2p, **bf), torch.zeros(b, self.k2p, self.k2p, **bf)
         self.has_precond = False
 
 
@@ -114,21 +125,28 @@ class Shampoo:
         self._pre = torch.zeros(n, **f32)
         self._mh = torch.zeros(n, **bf)
         self._ml = torch.zeros(n, **bf)
-        self._g16 = None
+        self._gh = self._gl = None   # bf16 hi/lo of fp32 gradients (allocated on first use)
         cap = self.params.max_preconditioner_dim
         self._gs: List[_GroupState] = [_GroupState(g, cap, dev) for g in store.mat_groups]
-        en = [(g, s) for g, s in zip(store.mat_groups, self._gs) if s.enabled]
-        max_t = max((g.batch * s.k1 * s.k2 for g, s in en), default=8)
-        max_z = max((g.batch * max(s.k1, s.k2) ** 2 for g, s in en), default=8)
-        max_b = max([g.batch for g in store.mat_groups] + [1])
-        self._T = torch.empty(max_t, **f32)
-        self._Th = torch.empty(max_t, **bf)
-        self._Tl = torch.empty(max_t, **bf)
-        self._Z = [torch.empty(max_z, **f32), torch.empty(max_z, **f32)]
-        self._Zh = torch.empty(max_z, **bf)
-        self._Zl = torch.empty(max_z, **bf)
-        self._n1 = torch.empty(max_b, **f32)
-        self._n2 = torch.empty(max_b, **f32)
+        lib = ops.lib()
+        ws = 256
+        for g, s in zip(store.mat_groups, self._gs):
+            ws = max(ws, int(lib.b200_shampoo_graft_workspace_bytes(g.batch)))
+            if s.enabled:
+                ws = max(ws, int(lib.b200_shampoo_root_workspace_bytes(g.batch, s.k1)),
+                         int(lib.b200_shampoo_root_workspace_bytes(g.batch, s.k2)),
+                         int(lib.b200_shampoo_precond_workspace_bytes(g.batch, s.k1, s.k2)))
+        # non-2-D parameters: consecutive equal-length entries are grafted as one batched call
+        self._vec_runs = []
+        for e in store.vec_entries:
+            run = self._vec_runs[-1] if self._vec_runs else None
+            if run is not None and run[1] == e.numel and e.numel % 8 == 0 and run[0] + run[1] * run[2] == e.offset:
+                run[2] += 1
+            else:
+                self._vec_runs.append([e.offset, e.numel, 1])
+        for _, _, cnt in self._vec_runs:
+            ws = max(ws, int(lib.b200_shampoo_graft_workspace_bytes(cnt)))
+        self._ws = torch.empty(ws, dtype=torch.uint8, device=dev)
         self.state = {}
         for name in store.index:
             self.state[name] = {"momentum": store.view(self._mom, name), "graft_m": store.view(self._gm, name),
@@ -136,50 +154,31 @@ class Shampoo:
         for g, s in zip(store.mat_groups, self._gs):
             if s.enabled:
                 for i, name in enumerate(g.names):
-                    self.state[name]["statistics.0"] = s.L[i]
-                    self.state[name]["statistics.1"] = s.R[i]
+                    st = self.state[name]
+                    st["statistics.0"] = s.L[i, :s.k1, :s.k1]
+                    st["statistics.1"] = s.R[i, :s.k2, :s.k2]
+                    st["preconditioners.0"] = s.PL[i, :s.k1, :s.k1]
+                    st["preconditioners.1"] = s.PR[i, :s.k2, :s.k2]
 
-    # ------------------------------------------------------------------------------------------
-    def _gemm3(self, a_mn, b_mn, M, N, K, batch, Ah, Al, lda, sA, Bh, Bl, ldb, sB, C, ldc, sC, D, ldd, sD,
-               alpha, beta, av=None, bv=None):
-        """D = alpha*(Ah Bh + Ah Bl + Al Bh) + beta*C  (fp32 out): bf16x3 product of two split matrices."""
-        ops.gemm_raw(a_mn, b_mn, M, N, K, batch, Ah, lda, sA, Bh, ldb, sB, C, ldc, sC, D, ldd, sD,
-                     alpha, beta, av, bv)
-        ops.gemm_raw(a_mn, b_mn, M, N, K, batch, Ah, lda, sA, Bl, ldb, sB, D, ldd, sD, D, ldd, sD,
-                     alpha, 1.0, av, None)
-        ops.gemm_raw(a_mn, b_mn, M, N, K, batch, Al, lda, sA, Bh, ldb, sB, D, ldd, sD, D, ldd, sD,
-                     alpha, 1.0, av, None)
-
-    def _inverse_pth_root(self, stat: torch.Tensor, Ph: torch.Tensor, Pl: torch.Tensor) -> None:
-        """MatrixSqrt.matrix_inverse_pth_root (shampoo.py:88-126), batched over stat [b,k,k]."""
+    def _inverse_pth_root(self, stat: torch.Tensor, P: torch.Tensor, Ph: torch.Tensor, Pl: torch.Tensor,
+                          k: int) -> None:
+        """MatrixSqrt.matrix_inverse_pth_root (shampoo.py:88-126), batched over stat [b, kp, kp]."""
         hp = self.params
-        b, k, _ = stat.shape
-        p = hp.exponent_override
-        kk = k * k
-        # tiny per-matrix scalars (trace, final scale) stay in torch; all k^3 work is tcgen05
-        diag = stat.diagonal(dim1=1, dim2=2)
-        tr = diag.sum(-1) + k * hp.preconditioner_epsilon
-        inv_tr = (1.0 / tr).contiguous()
-        scale_fin = tr.pow(-1.0 / (p * p)).contiguous()
-        Z, Z2 = self._Z[0][:b * kk], self._Z[1][:b * kk]
-        Zh, Zl = self._Zh[:b * kk], self._Zl[:b * kk]
-        # Z0 = (M + eps I)/tr  (elementwise set-up, once per update_period), then its bf16 hi/lo split
-        Z.copy_(((stat + hp.preconditioner_epsilon * torch.eye(k, device=stat.device)) *
-                 inv_tr[:, None, None]).reshape(-1))
-        ops.check(ops.lib().b200_split_bf16(Z.data_ptr(), k, Zh.data_ptr(), Zl.data_ptr(), k, b * k, k, 1.0, 0.0,
-                                            ops._stream()), "b200_split_bf16")
-        iters = 6
-        for it in range(iters):
-            last = it == iters - 1
-            av = scale_fin if last else None
-            self._gemm3(False, False, k, k, k, b, Zh, Zl, k, kk, Zh, Zl, k, kk, Z, k, kk, Z2, k, kk,
-                        1.0 / p, 1.0, av, av)
-            Z, Z2 = Z2, Z
-            if not last:
-                ops.check(ops.lib().b200_split_bf16(Z.data_ptr(), k, Zh.data_ptr(), Zl.data_ptr(), k, b * k, k,
-                                                    1.0, 0.0, ops._stream()), "b200_split_bf16")
-        ops.check(ops.lib().b200_split_bf16(Z.data_ptr(), k, Ph.data_ptr(), Pl.data_ptr(), k, b * k, k, 1.0, 0.0,
-                                            ops._stream()), "b200_split_bf16")
+        ops.shampoo_root(stat, P, Ph, Pl, k, hp.exponent_override, hp.preconditioner_epsilon, 6, self._ws)
+
+    @torch.no_grad()
+    def after_load(self) -> None:
+        """Called after a checkpoint's tensors were copied into `state`: rebuilds the derived bf16 hi/lo
+        operands of the preconditioners, so a resumed run is preconditioned from its first step
+        (reference: preconditioners are part of the saved state, shampoo.py:180-208, core/training.py:1354)."""
+        for s in getattr(self, "_gs", []):
+            if not s.enabled:
+                continue
+            for P, Ph, Pl in ((s.PL, s.PLh, s.PLl), (s.PR, s.PRh, s.PRl)):
+                ops.check(ops.lib().b200_split_bf16(P.data_ptr(), P.shape[-1], Ph.data_ptr(), Pl.data_ptr(),
+                                                    P.shape[-1], P.shape[0] * P.shape[1], P.shape[2], 1.0, 0.0,
+                                                    ops._stream()), "b200_split_bf16")
+            s.has_precond = bool(s.PL.any().item()) and bool(s.PR.any().item())
 
     # ------------------------------------------------------------------------------------------
     @torch.no_grad()
@@ -208,14 +207,15 @@ class Shampoo:
         # preconditioned blocks are overwritten below with -lr * PL mhat PR
         ops.ema_split(gsrc[:end], self._mom[:end], self._pre[:end], self._mh[:end], self._ml[:end], hp.beta1, gs,
                       inv_bc, -lr)
-        if gsrc.dtype != torch.bfloat16:
-            if self._g16 is None:
-                self._g16 = torch.empty(store.total, dtype=torch.bfloat16, device=store.device)
-            ops.check(ops.lib().b200_split_bf16(gsrc.data_ptr(), 8, self._g16.data_ptr(), None, 8,
+        if gsrc.dtype != torch.bfloat16 and store.mat_end > 0:
+            if self._gh is None:
+                self._gh = torch.empty(store.total, dtype=torch.bfloat16, device=store.device)
+                self._gl = torch.empty(store.total, dtype=torch.bfloat16, device=store.device)
+            ops.check(ops.lib().b200_split_bf16(gsrc.data_ptr(), 8, self._gh.data_ptr(), self._gl.data_ptr(), 8,
                                                 store.mat_end // 8, 8, 1.0, 0.0, ops._stream()), "b200_split_bf16")
-            g16 = self._g16
+            g_hi, g_lo = self._gh, self._gl
         else:
-            g16 = gsrc
+            g_hi, g_lo = gsrc, None
         decay = 1.0 - lr * hp.weight_decay if hp.weight_decay > 0.0 else 1.0
         do_root = t >= hp.start_preconditioning_step and t % hp.update_period == 0
         for g, s in zip(store.mat_groups, self._gs):
@@ -223,46 +223,26 @@ class Shampoo:
             b, c = g.batch, g.cols
             if s.enabled:
                 k1, k2 = s.k1, s.k2
-                G = g16[lo:lo + n]
-                a = (1.0 - hp.beta2) * gs * gs
-                ops.gemm_raw(False, False, k1, k1, k2, b, G, c, rc, G, c, rc, s.L, k1, k1 * k1, s.L, k1, k1 * k1,
-                             a, hp.beta2)
-                ops.gemm_raw(True, True, k2, k2, k1, b, G, c, rc, G, c, rc, s.R, k2, k2 * k2, s.R, k2, k2 * k2,
-                             a, hp.beta2)
+                ops.shampoo_stats(g_hi[lo:lo + n], None if g_lo is None else g_lo[lo:lo + n], c, rc, s.L, s.R, b, k1,
+                                  k2, hp.beta2, (1.0 - hp.beta2) * gs * gs)
                 if do_root:
-                    self._inverse_pth_root(s.L, s.PLh, s.PLl)
-                    self._inverse_pth_root(s.R, s.PRh, s.PRl)
+                    self._inverse_pth_root(s.L, s.PL, s.PLh, s.PLl, k1)
+                    self._inverse_pth_root(s.R, s.PR, s.PRh, s.PRl, k2)
                     s.has_precond = True
                 if t >= hp.start_preconditioning_step and s.has_precond:
-                    mh, ml = self._mh[lo:lo + n], self._ml[lo:lo + n]
-                    T, Th, Tl = self._T[:b * k1 * k2], self._Th[:b * k1 * k2], self._Tl[:b * k1 * k2]
-                    # T = PL @ mhat[:k1,:k2]   (mhat block read in place as an MN-major operand)
-                    self._gemm3(False, True, k1, k2, k1, b, s.PLh, s.PLl, k1, k1 * k1, mh, ml, c, rc,
-                                None, k2, k1 * k2, T, k2, k1 * k2, 1.0, 0.0)
-                    ops.check(ops.lib().b200_split_bf16(T.data_ptr(), k2, Th.data_ptr(), Tl.data_ptr(), k2, b * k1,
-                                                        k2, 1.0, 0.0, ops._stream()), "b200_split_bf16")
-                    # pre[:k1,:k2] = T @ PR  written straight into the update buffer (ldd = cols)
-                    pre = self._pre[lo:lo + n]
-                    self._gemm3(False, True, k1, k2, k2, b, Th, Tl, k2, k1 * k2, s.PRh, s.PRl, k2, k2 * k2,
-                                None, c, rc, pre, c, rc, -lr, 0.0)
-            self._graft_and_apply(store, lo, rc, b, lr, decay)
-        for e in store.vec_entries:
-            self._graft_and_apply(store, e.offset, e.numel, 1, lr, decay)
+                    # pre[:k1,:k2] = -lr * PL @ mhat[:k1,:k2] @ PR, written straight into the update buffer
+                    ops.shampoo_precond(s.PLh, s.PLl, s.PRh, s.PRl, self._mh[lo:lo + n], self._ml[lo:lo + n], c, rc,
+                                        self._pre[lo:lo + n], c, rc, b, k1, k2, -lr, self._ws)
+            self._graft_and_apply(store, lo, rc, b, decay)
+        for off, numel, cnt in self._vec_runs:
+            self._graft_and_apply(store, off, numel, cnt, decay)
 
-    def _graft_and_apply(self, store: ParamStore, lo: int, numel: int, batch: int, lr: float, decay: float) -> None:
+    def _graft_and_apply(self, store: ParamStore, lo: int, numel: int, batch: int, decay: float) -> None:
+        """_apply_grafting + parameter write (shampoo.py:297-312,365-373) for `batch` tensors of `numel`."""
         n = numel * batch
-        pre, d = self._pre[lo:lo + n], self._d[lo:lo + n]
-        n1, n2 = self._n1[:batch], self._n2[:batch]
-        ops.sumsq_raw(pre, n1, numel, batch)
-        ops.sumsq_raw(d, n2, numel, batch)
-        sn, gn = n1.sqrt(), n2.sqrt()      # ||upd|| with upd = -lr*pre (held in self._pre), ||graft step||
-        # _apply_grafting (shampoo.py:297-312): sn==0 -> graft step ; gn==0 -> upd ; else upd*(gn/sn).
-        # fp32 sqrt(sum(x^2)) overflows exactly like mx.linalg.norm would
-        coef = torch.where(sn == 0, torch.zeros_like(sn), torch.where(gn == 0, torch.ones_like(sn), gn / sn))
-        coef_d = (sn == 0).float()
         p16 = store.shadow[lo:lo + n] if store.mixed else None
-        ops.graft_update(store.master[lo:lo + n], p16, pre, d, numel, batch, coef.contiguous(), coef_d.contiguous(),
-                         decay)
+        ops.shampoo_graft(store.master[lo:lo + n], p16, self._pre[lo:lo + n], self._d[lo:lo + n], numel, batch,
+                          decay, self._ws)
 
     def apply_gradients(self, gradients, model):
         self.update(model, gradients)

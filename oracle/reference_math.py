@@ -457,3 +457,23 @@ def loss_and_grads(params: Dict[str, torch.Tensor], batch: torch.Tensor, d: Llam
     loss, ntoks = compute_loss(logits, batch[:, 1:], pad_token)
     loss.backward()
     return loss.detach(), int(ntoks), {k: v.grad for k, v in leaves.items()}
+
+
+def synthetic_batch_markov(step: int, rank: int, batch: int, seq: int, vocab: int) -> torch.Tensor:
+    """LEARNABLE synthetic tokens for loss-curve parity runs (uniform noise has the constant optimum
+    ln(vocab), so its curve cannot tell two optimizers apart): a fixed first-order Markov chain, every
+    token having 4 equally likely successors (table drawn once, seed 4242) with 10 % uniform noise;
+    per-step draws use the same seed rule as synthetic_batch.  Entropy rate ~ 0.9*ln4 + 0.1*ln(vocab) + H(0.1)."""
+    succ = torch.randint(0, vocab, (vocab, 4), generator=torch.Generator().manual_seed(4242), dtype=torch.int64)
+    g = torch.Generator().manual_seed(42 + 1000 * step + rank)
+    out = torch.empty((batch, seq + 1), dtype=torch.int64)
+    out[:, 0] = torch.randint(0, vocab, (batch,), generator=g, dtype=torch.int64)
+    choice = torch.randint(0, 4, (batch, seq), generator=g, dtype=torch.int64)
+    noisy = torch.rand((batch, seq), generator=g) < 0.1
+    rnd = torch.randint(0, vocab, (batch, seq), generator=g, dtype=torch.int64)
+    rows = torch.arange(batch)
+    for t in range(seq):
+        nxt = succ[out[:, t], choice[:, t]]
+        out[:, t + 1] = torch.where(noisy[:, t], rnd[:, t], nxt)
+    del rows
+    return out

@@ -461,3 +461,223 @@ def test_cross_entropy_fwd_bwd(ops, rows, V, ld):
     assert float(loss_rows[targets == pad].abs().max()) == 0.0
     assert rel(logits.grad[:, :V], ref_in.grad) < 4e-3
     assert torch.count_nonzero(logits.grad[:, V:]) == 0
+
+
+# ------------------------------------------------------------------------------------------------
+# Shampoo's Kronecker-factor path through the C ABI (b200_shampoo_*) against the REFERENCE's own
+# optimizers/shampoo.py outputs (tests/golden/make_golden.py).  Tolerance: fp32 matrices enter the tensor
+# cores as bf16 hi+lo pairs (hi*hi + hi*lo + lo*hi, fp32 accumulation): ~2^-16 per product, 1e-4 after the
+# six coupled iterations of the root.
+# ------------------------------------------------------------------------------------------------
+SH_TOL = 1e-4
+
+
+def _split(x):
+    hi = x.to(torch.bfloat16)
+    return hi.contiguous(), (x - hi.float()).to(torch.bfloat16).contiguous()
+
+
+def _padded(m, kp):
+    out = torch.zeros(1, kp, kp, device="cuda")
+    out[0, :m.shape[0], :m.shape[1]] = m
+    return out
+
+
+@pytest.mark.parametrize("p,key", [(0.75, "root_out_p075"), (0.5, "root_out_p05")])
+def test_shampoo_root_golden(ops, golden, p, key):
+    """b200_shampoo_root == MatrixSqrt.matrix_inverse_pth_root (optimizers/shampoo.py:88-126) on the
+    reference-generated SPD input, both exponents."""
+    m = torch.from_numpy(golden["root_in"]).cuda()
+    k = m.shape[0]                       # 40: already a multiple of 8
+    M = _padded(m, ops.rup8(k))
+    P = torch.empty_like(M)
+    Ph, Pl = torch.empty_like(M, dtype=torch.bfloat16), torch.empty_like(M, dtype=torch.bfloat16)
+    ops.shampoo_root(M, P, Ph, Pl, k, p, 1e-6, 6)
+    assert rel(P[0, :k, :k], golden[key]) < SH_TOL
+    assert rel(Ph.float() + Pl.float(), P) < 1e-5           # hi+lo carries ~16 bits of P
+    # the oracle restatement agrees too (it is what the whole-step tests use)
+    assert rel(P[0, :k, :k], R.matrix_inverse_pth_root(m.cpu(), p)) < SH_TOL
+
+
+def test_shampoo_root_unaligned_dimension(ops):
+    """k = 37 (stored zero-padded to 40, like the byte-level embedding's 259 -> 264): same result as the
+    oracle on the unpadded matrix, and the padding stays exactly zero."""
+    torch.manual_seed(21)
+    a = torch.randn(37, 64) * 0.3
+    m = a @ a.T
+    M = _padded(m.cuda(), 40)
+    P = torch.empty_like(M)
+    ops.shampoo_root(M, P, None, None, 37, 0.75, 1e-6, 6)
+    assert rel(P[0, :37, :37], R.matrix_inverse_pth_root(m, 0.75)) < SH_TOL
+    assert float(P[0, 37:].abs().max()) == 0.0 and float(P[0, :, 37:].abs().max()) == 0.0
+
+
+def test_shampoo_stats_root_precondition_golden(ops, golden):
+    """The three entry points chained exactly as Shampoo.update chains them, on the reference's inputs:
+    two statistics updates (g1, g2; beta2 0.95; 32 x 32 block of a [48, 40] gradient) -> roots -> PL g2 PR,
+    against the reference's statistics / preconditioners / preconditioned gradient."""
+    cap, b2 = 32, 0.95
+    L, Rm = torch.zeros(1, cap, cap, device="cuda"), torch.zeros(1, cap, cap, device="cuda")
+    for key in ("sh_g1", "sh_g2"):
+        gh, gl = _split(torch.from_numpy(golden[key]).cuda())
+        ops.shampoo_stats(gh, gl, 40, 48 * 40, L, Rm, 1, cap, cap, b2, 1 - b2)
+    assert rel(L[0], golden["sh_stat0"]) < 1e-5 and rel(Rm[0], golden["sh_stat1"]) < 1e-5
+    PL, PR = torch.empty_like(L), torch.empty_like(Rm)
+    hl = [torch.empty(1, cap, cap, device="cuda", dtype=torch.bfloat16) for _ in range(4)]
+    ops.shampoo_root(L, PL, hl[0], hl[1], cap, 0.75, 1e-6, 6)
+    ops.shampoo_root(Rm, PR, hl[2], hl[3], cap, 0.75, 1e-6, 6)
+    assert rel(PL[0], golden["sh_pre0"]) < SH_TOL and rel(PR[0], golden["sh_pre1"]) < SH_TOL
+    g2 = torch.from_numpy(golden["sh_g2"]).cuda()
+    mh, ml = _split(g2)
+    out = g2.clone().contiguous()        # pass-through part (rows >= 32, cols >= 32) must stay untouched
+    ops.shampoo_precond(hl[0], hl[1], hl[2], hl[3], mh, ml, 40, 48 * 40, out, 40, 48 * 40, 1, cap, cap, 1.0)
+    assert rel(out, golden["sh_preconditioned"]) < SH_TOL
+    assert torch.equal(out[cap:], g2[cap:]) and torch.equal(out[:, cap:], g2[:, cap:])
+
+
+def test_shampoo_graft_golden(ops, golden):
+    """b200_shampoo_graft == Shampoo._apply_grafting (shampoo.py:297-312) + the parameter write; edge cases
+    of the reference: zero Shampoo step -> grafting step, zero grafting step -> Shampoo step."""
+    gu = torch.from_numpy(golden["graft_in_graft"]).cuda().contiguous()
+    su = torch.from_numpy(golden["graft_in_shampoo"]).cuda().contiguous()
+    p = torch.zeros_like(su)
+    ops.shampoo_graft(p, None, su, gu, su.numel(), 1, 1.0)
+    assert rel(p, golden["graft_out"]) < 1e-6
+    p0 = torch.randn_like(su)
+    p = p0.clone()
+    p16 = torch.empty_like(p, dtype=torch.bfloat16)
+    ops.shampoo_graft(p, p16, torch.zeros_like(su), gu, su.numel(), 1, 0.99)
+    assert rel(p, p0 * 0.99 + gu) < 1e-6 and rel(p16, p) < 4e-3
+    p = p0.clone()
+    ops.shampoo_graft(p, None, su, torch.zeros_like(gu), su.numel(), 1, 1.0)
+    assert rel(p, p0 + su) < 1e-6
+    # batched: per-matrix norms
+    up, gr = torch.randn(3, 16, 24, device="cuda"), torch.randn(3, 16, 24, device="cuda") * 0.1
+    p = torch.zeros_like(up)
+    ops.shampoo_graft(p, None, up, gr, 16 * 24, 3, 1.0)
+    ref = up * (gr.flatten(1).norm(dim=1) / up.flatten(1).norm(dim=1))[:, None, None]
+    assert rel(p, ref) < 1e-6
+    # deterministic reductions: bit-identical on repetition (replica equality under data parallelism)
+    q = torch.zeros_like(up)
+    ops.shampoo_graft(q, None, up, gr, 16 * 24, 3, 1.0)
+    assert torch.equal(p, q)
+
+
+def test_shampoo_optimizer_steps_golden_and_oracle(ops, golden):
+    """Product Shampoo.update(model, gradients) with fp32 gradients: (1) after the reference's two gradients
+    its state holds the reference's statistics AND preconditioners; (2) three further steps against
+    ShampooOracle on a well-conditioned case whose grafted step is NON-zero (finite preconditioned norm)."""
+    from mlx_cuda_distributed_pretraining_b200.optimizers.shampoo import Shampoo, ShampooParams
+
+    class Tiny(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            torch.manual_seed(31)
+            self.w = torch.nn.Parameter(torch.randn(48, 40) * 0.1)
+            self.gain = torch.nn.Parameter(torch.ones(40))
+
+    model = Tiny().cuda()
+    hp = dict(beta2=0.95, start_preconditioning_step=1, update_period=1, max_preconditioner_dim=32)
+    opt = Shampoo(learning_rate=0.01, params=ShampooParams(**hp))
+    oracle = R.ShampooOracle(0.01, R.ShampooParams(**hp))
+    ref = {"w": model.w.detach().cpu().clone(), "gain": model.gain.detach().cpu().clone()}
+    torch.manual_seed(32)
+    grads = [{"w": torch.from_numpy(golden["sh_g1"]), "gain": torch.randn(40) * 0.05},
+             {"w": torch.from_numpy(golden["sh_g2"]), "gain": torch.randn(40) * 0.05}]
+    grads += [{"w": torch.randn(48, 40) * 0.05, "gain": torch.randn(40) * 0.05} for _ in range(3)]
+    for step, g in enumerate(grads):
+        before = {k: v.clone() for k, v in ref.items()}
+        got_before = {"w": model.w.detach().cpu().clone(), "gain": model.gain.detach().cpu().clone()}
+        opt.update(model, {k: v.cuda() for k, v in g.items()})
+        oracle.update(ref, {k: v.clone() for k, v in g.items()})
+        if step == 1:
+            st = opt.state["w"]
+            assert rel(st["statistics.0"], golden["sh_stat0"]) < 1e-5 and rel(st["statistics.1"], golden["sh_stat1"]) < 1e-5
+            assert rel(st["preconditioners.0"], golden["sh_pre0"]) < SH_TOL
+            assert rel(st["preconditioners.1"], golden["sh_pre1"]) < SH_TOL
+        for k in ref:
+            d_ref = ref[k] - before[k]
+            d_got = getattr(model, k).detach().cpu() - got_before[k]
+            assert float(d_ref.norm()) > 0 and torch.isfinite(d_ref).all(), (step, k)   # the step is NOT zeroed
+            assert rel(d_got, d_ref) < 2e-3, (step, k, rel(d_got, d_ref))
+        # keep the two trajectories glued (compare per-step updates, not accumulated drift)
+        with torch.no_grad():
+            model.w.copy_(ref["w"].cuda())
+            model.gain.copy_(ref["gain"].cuda())
+            store = model._b200_store
+            store.view(store.master, "w").copy_(ref["w"].cuda())
+            store.view(store.master, "gain").copy_(ref["gain"].cuda())
+    assert opt.count == len(grads)
+
+
+def test_shampoo_unaligned_factor_is_preconditioned(ops):
+    """A [259, 64]-style block (byte-level embedding): rows 259 -> factor stored [264, 264]; the preconditioned
+    step matches the oracle (previous round skipped such blocks)."""
+    from mlx_cuda_distributed_pretraining_b200.optimizers.shampoo import Shampoo, ShampooParams
+
+    class Tiny(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            torch.manual_seed(33)
+            self.emb = torch.nn.Parameter(torch.randn(37, 24) * 0.1)
+
+    model = Tiny().cuda()
+    hp = dict(beta2=0.95, start_preconditioning_step=1, update_period=1, max_preconditioner_dim=1024)
+    opt = Shampoo(learning_rate=0.01, params=ShampooParams(**hp))
+    assert opt is not None
+    oracle = R.ShampooOracle(0.01, R.ShampooParams(**hp))
+    ref = {"emb": model.emb.detach().cpu().clone()}
+    torch.manual_seed(34)
+    for step in range(2):
+        g = torch.randn(37, 24) * 0.05
+        before = ref["emb"].clone()
+        opt.update(model, {"emb": g.cuda()})
+        oracle.update(ref, {"emb": g.clone()})
+        d_ref = ref["emb"] - before
+        d_got = model.emb.detach().cpu() - before
+        assert float(d_ref.norm()) > 0
+        assert rel(d_got, d_ref) < 2e-3, (step, rel(d_got, d_ref))
+        with torch.no_grad():
+            store = model._b200_store
+            store.view(store.master, "emb").copy_(ref["emb"].cuda())
+            model.emb.copy_(ref["emb"].cuda())
+    assert opt.state["emb"]["statistics.0"].shape == (37, 37)
+    assert opt.state["emb"]["preconditioners.1"].shape == (24, 24)
+
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE shapes: attention at S = 2048 (C3 / C4 / C5 dims) and Newton-Schulz at C5's 2048-wide matrices
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,S,H,Hk,D", [(16, 2048, 16, 8, 64),    # C3 per-GPU micro-batch (GQA 16/8)
+                                        (8, 2048, 16, 16, 64),    # C4 dims (MHA), 1/8 of its batch
+                                        (4, 2048, 16, 16, 128)])  # C5 dims (D = 128, 16 key tiles), 1/8 of its batch
+def test_attention_baseline_shapes_vs_oracle(ops, B, S, H, Hk, D):
+    """Forward and backward at the BASELINE attention shapes (arch/flash_attention.py:78-156 at the C3/C4/C5
+    dims).  The kernel runs the FULL launch; the oracle (dense fp32 softmax(QK^T)V + autograd, ~1 GB of scores
+    per batch row) is evaluated on the first and last batch rows -- rows are independent, so this checks every
+    (tile, head) code path of the full-size grid."""
+    torch.manual_seed(40 + D)
+    q = torch.randn(B, S, H, D, device="cuda").to(torch.bfloat16).requires_grad_(True)
+    k = torch.randn(B, S, Hk, D, device="cuda").to(torch.bfloat16).requires_grad_(True)
+    v = torch.randn(B, S, Hk, D, device="cuda").to(torch.bfloat16).requires_grad_(True)
+    o = ops.attention(q, k, v, D ** -0.5, True)
+    do = torch.randn_like(o)
+    o.backward(do)
+    mask = R.causal_mask(S)
+    for b in (0, B - 1):
+        qr, kr, vr = (t[b:b + 1].detach().float().cpu().requires_grad_(True) for t in (q, k, v))
+        orf = R.attention(qr, kr, vr, D ** -0.5, mask)
+        orf.backward(do[b:b + 1].float().cpu())
+        errs = (rel(o[b:b + 1], orf), rel(q.grad[b:b + 1], qr.grad), rel(k.grad[b:b + 1], kr.grad),
+                rel(v.grad[b:b + 1], vr.grad))
+        assert max(errs) < 1e-2, (b, errs)
+
+
+@pytest.mark.parametrize("shape", [(1, 2048, 2048), (2, 2048, 5632), (1, 5632, 2048)])
+def test_newton_schulz_c5_shapes(ops, shape):
+    """m = 2048 (C5's hidden size): X is stored bf16 between iterations, so the error budget is checked at the
+    widest matrices of the BASELINE configs too (fp32 oracle; fp64 would take minutes on the host)."""
+    torch.manual_seed(50)
+    g = torch.randn(*shape) * 0.02
+    x = ops.zeropower_via_newtonschulz5(g.cuda())
+    assert rel(x, R.newton_schulz5(g)) < 3e-2

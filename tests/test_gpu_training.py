@@ -269,3 +269,61 @@ def test_two_gpu_data_parallel_matches_mean_of_gradients(tmp_path):
     got = masters(tr)
     # DP sums bf16 gradients over NCCL; the single-process twin accumulates them in fp32
     assert max(rel(dpw[n], got[n]) for n in got) < 5e-3
+
+
+@pytest.mark.parametrize("optimizer", ["hybrid", "shampoo"])
+def test_resume_restores_full_optimizer_state(tmp_path, optimizer):
+    """Save at step 3, resume in a fresh Trainer: every optimizer tensor (momentum / Adam moments / Shampoo
+    statistics AND preconditioners), both step counters of the hybrid optimizer, and -- the point of saving the
+    preconditioners (reference state: optimizers/shampoo.py:180-208, saved by core/training.py:1354-1356) -- the
+    next step of the resumed run equals the next step of the uninterrupted run bit for bit."""
+    from safetensors.torch import load_file
+    from mlx_cuda_distributed_pretraining_b200.core.training import Config, Trainer
+    opt_cfg = {"optimizer": optimizer}
+    if optimizer == "shampoo":
+        opt_cfg.update(start_preconditioning_step=2, update_period=2, beta2=0.95)   # roots at t = 2; t = 3, 4 reuse/refresh
+    over = {"training__optimization": opt_cfg, "hp__iters": 8,
+            "logging__steps": {"logging_interval": 10 ** 9, "checkpoint_interval": 3, "validation_interval": 0}}
+    tr = make_trainer(tmp_path, **over)
+    for step in range(3):
+        tr.train_step(step, tr.data_manager.generate_batch(step))
+    tr.save_checkpoint(3)
+    saved = load_file(str(tmp_path / "smoke" / "checkpoints" / "step_3_optimizer.safetensors"))
+    if optimizer == "shampoo":
+        assert any(k.endswith("preconditioners.0") for k in saved) and any(k.endswith("statistics.1") for k in saved)
+        assert any(float(v.abs().sum()) > 0 for k, v in saved.items() if k.endswith("preconditioners.0"))
+    else:
+        assert "alt_count" in saved and int(saved["alt_count"]) == 3
+    tr.train_step(3, tr.data_manager.generate_batch(3))          # the uninterrupted run's 4th step
+    want = masters(tr)
+
+    cfg = tiny_config(**over)
+    cfg["resume"] = {"checkpoint": str(tmp_path / "smoke" / "checkpoints" / "step_3")}
+    tr2 = Trainer(Config.from_dict(cfg), synthetic=True, quiet=True, run_root=str(tmp_path / "resumed"))
+    tr2._accum_step, tr2._accum_tokens = 0, 0
+    assert tr2.load_checkpoint(cfg["resume"]["checkpoint"]) == 3
+    assert tr2.optimizer.count == 3
+    own = tr2.optimizer.state_dict()
+    for n, t in saved.items():
+        if n in own and own[n].is_cuda:
+            assert torch.equal(own[n].detach().cpu(), t), n
+    if optimizer == "hybrid":
+        assert tr2.optimizer.non_matrix_optimizer.count == 3
+    tr2.train_step(3, tr2.data_manager.generate_batch(3))
+    got = masters(tr2)
+    assert all(torch.equal(got[n], want[n]) for n in want), [n for n in want if not torch.equal(got[n], want[n])][:3]
+
+
+def test_explicit_batch_path_never_reuses_a_pinned_buffer_in_flight(tmp_path):
+    """Trainer._to_device (validation and the B200_PREFETCH=0 path): back-to-back host batches, no sync in
+    between, must reach the device intact even when the CPU runs ahead of the GPU."""
+    tr = make_trainer(tmp_path, optimizer="adamw")
+    batches = [tr.data_manager.generate_batch(s) for s in range(12)]
+    spin = torch.empty(64 << 20, device="cuda")
+    devs = []
+    for b in batches:
+        for _ in range(4):
+            spin.add_(1.0)              # keep the stream busy so the copies queue up behind compute
+        devs.append(tr._to_device(b))
+    torch.cuda.synchronize()
+    assert all(torch.equal(d.cpu(), b) for d, b in zip(devs, batches))
