@@ -629,6 +629,12 @@ class Trainer:
             if batch is None:
                 batch = self.data_manager.generate_batch(step)
             dev_batch = self._to_device(batch)
+        return self.micro_step(step, dev_batch)
+
+    def micro_step(self, step: int, dev_batch: torch.Tensor):
+        """Forward + backward of one micro-batch already resident on the device, gradient clamp / 1/k
+        accumulation (core/training.py:1664-1696), and -- on the k-th micro-step -- the data-parallel
+        exchange and the optimizer update.  Returns (loss, ntoks, did_update)."""
         loss, ntoks = self.compute_loss(self.model, dev_batch[:, :-1], dev_batch[:, 1:])
         loss.backward()
         k = self.grad_accum_steps

@@ -54,6 +54,23 @@ class Muon:
         self.shard_ns = False         # owner-computes Newton-Schulz across data-parallel ranks
         self._store: Optional[ParamStore] = None
         self._buf = None
+        self._exchange = "auto"       # see set_exchange()
+        self._xg = self._xg_handles = None
+        self._use_multicast = False
+
+    def set_exchange(self, mode: str) -> str:
+        """Select the owner-computes exchange at run time (bench.py's cross-check of the implementations):
+        "auto" (peer stores; NVSwitch multicast from 4 ranks up), "unicast", "multicast", or "nccl" (equal-chunk
+        ownership + all_gather_into_tensor).  Returns the mode actually in effect."""
+        if mode not in ("auto", "unicast", "multicast", "nccl"):
+            raise ValueError(f"unknown exchange mode {mode}")
+        self._exchange = mode
+        self._plan_world = None
+        if self._xg_handles is not None and mode != "nccl":
+            world = dp.world_size()
+            mc_ok = all(int(getattr(h, "multicast_ptr", 0) or 0) != 0 for h in self._xg_handles)
+            self._use_multicast = mc_ok and (mode == "multicast" or (mode == "auto" and world >= 4))
+        return self.exchange_mode
 
     # -- reference surface ---------------------------------------------------------------------
     @property
@@ -114,7 +131,7 @@ class Muon:
         rank = dp.env_rank_world()[0] if world > 1 else 0
         if world > 1 and self._xg is None:
             self._alloc_gather_buffers(store, world)
-        p2p = world > 1 and self._xg_handles is not None
+        p2p = world > 1 and self._xg_handles is not None and self._exchange != "nccl"
         pending = []
         # experimental (B200_NS_STREAMS=2, single process): run the shape groups' chains alternately on two
         # side streams so that one group's tail wave is filled by the other group's tiles
@@ -262,7 +279,7 @@ class Muon:
     def exchange_mode(self) -> str:
         if not self.shard_ns or self._xg is None:
             return "replicated" if not self.shard_ns else "sharded (not started)"
-        if self._xg_handles is None:
+        if self._xg_handles is None or self._exchange == "nccl":
             return "NCCL all-gather"
         return ("fused GEMM+all-gather, NVSwitch multicast stores" if self._use_multicast
                 else "fused GEMM+all-gather, unicast peer stores")
@@ -273,7 +290,7 @@ class Muon:
         rank runs one or two long batched chains instead of 3-matrix slivers of every group); the NCCL
         exchange needs the equal-chunk split of `owned_ranges`."""
         g = self._store.mat_groups[gi]
-        if world <= 1 or self._xg_handles is None:
+        if world <= 1 or self._xg_handles is None or self._exchange == "nccl":
             return self.owned_ranges(g.batch, world, rank)
         if getattr(self, "_plan_world", None) != world:
             def cost(r, c):

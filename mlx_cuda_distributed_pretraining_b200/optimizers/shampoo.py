@@ -223,16 +223,22 @@ class Shampoo:
             b, c = g.batch, g.cols
             if s.enabled:
                 k1, k2 = s.k1, s.k2
+                tok = ops._t0("shampoo_stats")
                 ops.shampoo_stats(g_hi[lo:lo + n], None if g_lo is None else g_lo[lo:lo + n], c, rc, s.L, s.R, b, k1,
                                   k2, hp.beta2, (1.0 - hp.beta2) * gs * gs)
+                ops._t1(tok)
                 if do_root:
+                    tok = ops._t0("shampoo_root")
                     self._inverse_pth_root(s.L, s.PL, s.PLh, s.PLl, k1)
                     self._inverse_pth_root(s.R, s.PR, s.PRh, s.PRl, k2)
+                    ops._t1(tok)
                     s.has_precond = True
                 if t >= hp.start_preconditioning_step and s.has_precond:
                     # pre[:k1,:k2] = -lr * PL @ mhat[:k1,:k2] @ PR, written straight into the update buffer
+                    tok = ops._t0("shampoo_precond")
                     ops.shampoo_precond(s.PLh, s.PLl, s.PRh, s.PRl, self._mh[lo:lo + n], self._ml[lo:lo + n], c, rc,
                                         self._pre[lo:lo + n], c, rc, b, k1, k2, -lr, self._ws)
+                    ops._t1(tok)
             self._graft_and_apply(store, lo, rc, b, decay)
         for off, numel, cnt in self._vec_runs:
             self._graft_and_apply(store, off, numel, cnt, decay)
