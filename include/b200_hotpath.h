@@ -78,6 +78,25 @@ int b200_newton_schulz_allgather(const void* x_in, void* x_out, int batch, int r
  * counters.  The reductions are DETERMINISTIC (fixed summation order, no float atomics), so data-parallel
  * replicas that hold identical gradients compute bit-identical norms and stay bit-identical. */
 size_t b200_reduce_workspace_bytes(int batch);
+/* Whole-model chain: all shape groups of the optimizer advance through the iteration together and every stage
+ * (A = X X^T | B = bA + cAA | X' = aX + BX) is ONE grouped tcgen05 launch over all groups -- 3 launches per
+ * iteration instead of 3 per group (muon.py:91 loops over parameters).  Per group the arguments mean what they
+ * mean in b200_newton_schulz / _allgather; n_groups <= 6 takes the grouped path (each group min(rows, cols) > 128),
+ * anything else falls back to per-group chains.  Results are identical to per-group calls up to the fp32
+ * summation order of split-K partials. */
+typedef struct b200_ns_group {
+  const void* x_in;            /* bf16 [batch, rows, cols], un-normalised */
+  void* x_out;                 /* bf16 [batch, rows, cols] */
+  int batch, rows, cols;
+  const float* inv_norm;       /* [batch] 1/(||x||_F + eps) */
+  const float* inv_norm_sq;    /* [batch] its square */
+  const void* const* peer_out; /* HOST array of n_peers peer-mapped copies of x_out (NULL when n_peers == 0) */
+  int n_peers;
+} b200_ns_group;
+size_t b200_newton_schulz_multi_workspace_bytes(const b200_ns_group* groups, int n_groups, int steps);
+int b200_newton_schulz_multi(const b200_ns_group* groups, int n_groups, int steps, float a, float b, float c,
+                             void* workspace, size_t workspace_bytes, void* stream);
+
 /* muon.py:101,105: buf = (1-mu)*g*gscale + mu*buf ; u = nesterov ? g*gscale + mu*buf : buf.
  * g: [batch,numel] bf16 (g_is_bf16=1) or f32; buf f32; u bf16; sumsq[b] = sum(u_b^2) (overwritten). */
 int b200_muon_momentum(const void* g, int g_is_bf16, float* buf, void* u_bf16, float* sumsq,

@@ -63,6 +63,17 @@ SIGNATURES = {
     "b200_attn_bwd_strided": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _i, _i, _vp, _sz, _vp]),
 }
 
+
+
+class NsGroup(C.Structure):
+    """b200_ns_group (include/b200_hotpath.h)"""
+    _fields_ = [("x_in", _vp), ("x_out", _vp), ("batch", _i), ("rows", _i), ("cols", _i), ("inv_norm", _vp),
+                ("inv_norm_sq", _vp), ("peer_out", C.POINTER(_vp)), ("n_peers", _i)]
+
+
+SIGNATURES["b200_newton_schulz_multi_workspace_bytes"] = (_sz, [C.POINTER(NsGroup), _i, _i])
+SIGNATURES["b200_newton_schulz_multi"] = (_i, [C.POINTER(NsGroup), _i, _i, _f, _f, _f, _vp, _sz, _vp])
+
 _lib = None
 
 

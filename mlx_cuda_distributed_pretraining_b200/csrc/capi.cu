@@ -13,6 +13,18 @@ size_t newton_schulz_workspace_bytes(int batch, int rows, int cols, int steps);
 int newton_schulz(const void* x_in, void* x_out, int batch, int rows, int cols, int steps, float a,
                   float b, float c, const float* inv_norm, const float* inv_norm_sq, void* ws,
                   size_t ws_bytes, const void* const* peer_out, int n_peers, cudaStream_t stream);
+struct NsGroup {
+  const void* x_in;
+  void* x_out;
+  int batch, rows, cols;
+  const float* inv_norm;
+  const float* inv_norm_sq;
+  const void* const* peer_out;
+  int n_peers;
+};
+size_t newton_schulz_multi_workspace_bytes(const NsGroup* g, int n, int steps);
+int newton_schulz_multi(const NsGroup* g, int n, int steps, float a, float b, float c, void* ws, size_t ws_bytes,
+                        cudaStream_t stream);
 size_t reduce_workspace_bytes(int batch);
 int muon_momentum(const void* g, int g_is_bf16, float* buf, void* u_bf16, float* sumsq,
                   long long numel, int batch, float mu, int nesterov, float gscale, void* ws,
@@ -119,6 +131,15 @@ int b200_newton_schulz_allgather(const void* x_in, void* x_out, int batch, int r
                                  int n_peers, void* stream) {
   return b200::newton_schulz(x_in, x_out, batch, rows, cols, steps, a, b, c, inv_norm, inv_norm_sq,
                              workspace, workspace_bytes, peer_out, n_peers, S_(stream));
+}
+static_assert(sizeof(b200_ns_group) == sizeof(b200::NsGroup), "b200_ns_group layout");
+size_t b200_newton_schulz_multi_workspace_bytes(const b200_ns_group* groups, int n_groups, int steps) {
+  return b200::newton_schulz_multi_workspace_bytes(reinterpret_cast<const b200::NsGroup*>(groups), n_groups, steps);
+}
+int b200_newton_schulz_multi(const b200_ns_group* groups, int n_groups, int steps, float a, float b, float c,
+                             void* workspace, size_t workspace_bytes, void* stream) {
+  return b200::newton_schulz_multi(reinterpret_cast<const b200::NsGroup*>(groups), n_groups, steps, a, b, c, workspace,
+                                   workspace_bytes, S_(stream));
 }
 size_t b200_reduce_workspace_bytes(int batch) { return b200::reduce_workspace_bytes(batch); }
 int b200_muon_momentum(const void* g, int g_is_bf16, float* buf, void* u_bf16, float* sumsq,

@@ -51,4 +51,28 @@ int make_tensor_map(CUtensorMap* out, const void* base, CUtensorMapDataType dtyp
 
 int num_sms();
 
+// One problem of a grouped CTA-pair GEMM launch (gemm_tc2.cu: gemm_grouped_2cta): D = alpha*av[b]*op(A)op(B) +
+// beta*bv[b]*C, bf16 in/out, batched; layouts as in b200_gemm_bf16.
+struct GroupedGemm {
+  bool a_mn, b_mn;
+  int M, N, K, batch;
+  const void* A;
+  long long lda, strideA;
+  const void* B;
+  long long ldb, strideB;
+  const void* C;
+  long long ldc, strideC;
+  void* D;
+  long long ldd, strideD;
+  float alpha, beta;
+  const float* alpha_vec;
+  const float* beta_vec;
+  int symmetric;     // D == D^T asserted by the caller: compute the upper triangle of tiles, mirror the rest
+  int k_splits;      // > 1: split-K into fp32 slabs `splitk_ws` ([k_splits][batch][M][N]) + finalize
+  float* splitk_ws;
+  const void* const* peer_D;  // GEMM -> all-gather: peer-mapped copies of D (n_peers <= 7)
+  int n_peers;
+};
+int gemm_grouped_2cta(const GroupedGemm* probs, int n, cudaStream_t stream);
+
 }  // namespace b200

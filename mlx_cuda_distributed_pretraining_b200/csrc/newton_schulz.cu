@@ -29,6 +29,17 @@ int gemm_bf16_2cta(bool a_mn, bool b_mn, int M, int N, int K, int batch, const v
 
 static inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
 
+// One shape group of the whole-model chain (mirrors b200_ns_group of the public header)
+struct NsGroup {
+  const void* x_in;
+  void* x_out;
+  int batch, rows, cols;
+  const float* inv_norm;
+  const float* inv_norm_sq;
+  const void* const* peer_out;
+  int n_peers;
+};
+
 // G1 of a lone big matrix (the 32003 x 1024 embedding: 10 symmetric tiles, K = 32003) would occupy a
 // fraction of the CTA pairs for hundreds of microseconds.  Cut K so that every pair gets a work item.
 static int g1_k_splits(int batch, int m, int k) {
@@ -141,6 +152,204 @@ int newton_schulz(const void* x_in, void* x_out, int batch, int rows, int cols, 
     }
     if (rc_) return rc_;
     cur = nxt;
+  }
+  return B200_OK;
+}
+
+
+// ---------------------------------------------------------------------------------------------------------
+// Whole-model chain: every shape group of the optimizer advances through the SAME iteration together, so each
+// stage (A = X X^T | B = bA + cAA | X' = aX + BX) is ONE grouped launch over all groups (gemm_tc2.cu) instead of
+// one launch per group: 3 launches per iteration (+ one split-K finalize for a lone tall matrix) instead of
+// 3 x groups, and the per-launch wave tail is amortised over all groups' tiles (C2: 682 instead of 240 tiles
+// for the B stage on 74 CTA pairs).  Falls back to the per-group chain when a group is too small for the
+// CTA-pair kernel (min(rows, cols) <= 128) or there are more groups than one launch takes.
+// ---------------------------------------------------------------------------------------------------------
+static bool multi_grouped_ok(const NsGroup* g, int n) {
+  static const bool off = [] {
+    const char* e = getenv("B200_NS_GROUPED");
+    return e != nullptr && e[0] == '0';
+  }();
+  if (off || n < 1 || n > 6 || num_sms() < 2) return false;
+  for (int i = 0; i < n; ++i) {
+    const int m = g[i].rows < g[i].cols ? g[i].rows : g[i].cols;
+    if (m <= 128 || (m & 7) != 0 || (g[i].cols & 7) != 0) return false;
+  }
+  return true;
+}
+
+struct NsLayout {  // workspace slices of one group
+  size_t a, b, xtmp, splitk, end;
+  int splits;
+};
+static NsLayout ns_layout(const NsGroup& g, int steps, size_t base) {
+  const size_t m = g.rows < g.cols ? g.rows : g.cols;
+  NsLayout l;
+  l.a = base;
+  l.b = l.a + align256((size_t)g.batch * m * m * 2);
+  l.xtmp = l.b + align256((size_t)g.batch * m * m * 2);
+  l.splitk = l.xtmp + (steps >= 2 ? align256((size_t)g.batch * g.rows * g.cols * 2) : 0);
+  l.splits = g1_k_splits(g.batch, (int)m, g.rows < g.cols ? g.cols : g.rows);
+  l.end = l.splitk + (l.splits > 1 ? align256((size_t)l.splits * g.batch * m * m * 4) : 0);
+  return l;
+}
+
+size_t newton_schulz_multi_workspace_bytes(const NsGroup* g, int n, int steps) {
+  size_t off = 0;
+  for (int i = 0; i < n; ++i) {
+    const size_t grouped_end = ns_layout(g[i], steps, off).end;
+    const size_t single_end = off + newton_schulz_workspace_bytes(g[i].batch, g[i].rows, g[i].cols, steps);
+    off = grouped_end > single_end ? grouped_end : single_end;
+  }
+  return off;
+}
+
+int newton_schulz_multi(const NsGroup* g, int n, int steps, float a, float b, float c, void* ws, size_t ws_bytes,
+                        cudaStream_t stream) {
+  B200_CHECK_ARG(n >= 1 && g != nullptr && steps > 0, "newton_schulz_multi: bad arguments (n=%d steps=%d)", n, steps);
+  for (int i = 0; i < n; ++i) {
+    B200_CHECK_ARG(g[i].batch > 0 && g[i].rows > 0 && g[i].cols > 0 && g[i].cols % 8 == 0,
+                   "newton_schulz_multi: group %d has a bad shape batch=%d rows=%d cols=%d", i, g[i].batch, g[i].rows,
+                   g[i].cols);
+    B200_CHECK_ARG(g[i].x_in != g[i].x_out, "newton_schulz_multi: group %d: x_in and x_out must be distinct", i);
+    B200_CHECK_ARG(g[i].n_peers >= 0 && g[i].n_peers <= 7 && (g[i].n_peers == 0 || g[i].peer_out != nullptr),
+                   "newton_schulz_multi: group %d: bad peer list", i);
+  }
+  if (ws_bytes < newton_schulz_multi_workspace_bytes(g, n, steps)) {
+    set_error("newton_schulz_multi: workspace too small (%zu < %zu)", ws_bytes,
+              newton_schulz_multi_workspace_bytes(g, n, steps));
+    return B200_ERR_WORKSPACE;
+  }
+  char* w = reinterpret_cast<char*>(ws);
+  if (!multi_grouped_ok(g, n)) {
+    size_t off = 0;
+    for (int i = 0; i < n; ++i) {
+      const size_t grouped_end = ns_layout(g[i], steps, off).end;
+      const size_t need = newton_schulz_workspace_bytes(g[i].batch, g[i].rows, g[i].cols, steps);
+      int rc = newton_schulz(g[i].x_in, g[i].x_out, g[i].batch, g[i].rows, g[i].cols, steps, a, b, c, g[i].inv_norm,
+                             g[i].inv_norm_sq, w + off, need, g[i].peer_out, g[i].n_peers, stream);
+      if (rc) return rc;
+      off = grouped_end > off + need ? grouped_end : off + need;
+    }
+    return B200_OK;
+  }
+  NsLayout lay[6];
+  const void* cur[6];
+  {
+    size_t off = 0;
+    for (int i = 0; i < n; ++i) {
+      lay[i] = ns_layout(g[i], steps, off);
+      const size_t single_end = off + newton_schulz_workspace_bytes(g[i].batch, g[i].rows, g[i].cols, steps);
+      off = lay[i].end > single_end ? lay[i].end : single_end;
+      cur[i] = g[i].x_in;
+    }
+  }
+  GroupedGemm pr[6];
+  for (int it = 0; it < steps; ++it) {
+    const bool first = it == 0, last = it == steps - 1;
+    // ---- G1: A = X X^T (wide) / X^T X (tall), symmetric; iteration 1 carries 1/(||G||+eps)^2 ----
+    for (int i = 0; i < n; ++i) {
+      const bool tall = g[i].rows > g[i].cols;
+      const int m = tall ? g[i].cols : g[i].rows;
+      const long long rc_ = (long long)g[i].rows * g[i].cols, mm = (long long)m * m;
+      GroupedGemm& q = pr[i];
+      q = GroupedGemm{};
+      q.a_mn = tall;
+      q.b_mn = tall;
+      q.M = m;
+      q.N = m;
+      q.K = tall ? g[i].rows : g[i].cols;
+      q.batch = g[i].batch;
+      q.A = cur[i];
+      q.lda = g[i].cols;
+      q.strideA = rc_;
+      q.B = cur[i];
+      q.ldb = g[i].cols;
+      q.strideB = rc_;
+      q.D = w + lay[i].a;
+      q.ldd = m;
+      q.strideD = mm;
+      q.alpha = 1.0f;
+      q.beta = 0.0f;
+      q.alpha_vec = first ? g[i].inv_norm_sq : nullptr;
+      q.symmetric = kSym ? 1 : 0;
+      q.k_splits = lay[i].splits;
+      q.splitk_ws = reinterpret_cast<float*>(w + lay[i].splitk);
+    }
+    int rc = gemm_grouped_2cta(pr, n, stream);
+    if (rc) return rc;
+    // ---- G2: B = b A + c A A (A symmetric: A A^T with both operands K-major) ----
+    for (int i = 0; i < n; ++i) {
+      const int m = g[i].rows > g[i].cols ? g[i].cols : g[i].rows;
+      const long long mm = (long long)m * m;
+      GroupedGemm& q = pr[i];
+      q = GroupedGemm{};
+      q.M = q.N = q.K = m;
+      q.batch = g[i].batch;
+      q.A = q.B = q.C = w + lay[i].a;
+      q.lda = q.ldb = q.ldc = q.ldd = m;
+      q.strideA = q.strideB = q.strideC = q.strideD = mm;
+      q.D = w + lay[i].b;
+      q.alpha = c;
+      q.beta = b;
+      q.symmetric = kSym ? 1 : 0;
+      q.k_splits = 1;
+    }
+    rc = gemm_grouped_2cta(pr, n, stream);
+    if (rc) return rc;
+    // ---- G3: X' = a X + B X (wide) / a X + X B (tall); the last one carries the peer stores ----
+    for (int i = 0; i < n; ++i) {
+      const bool tall = g[i].rows > g[i].cols;
+      const int m = tall ? g[i].cols : g[i].rows;
+      const long long rc_ = (long long)g[i].rows * g[i].cols, mm = (long long)m * m;
+      void* nxt = ((steps - 1 - it) % 2 == 0) ? g[i].x_out : static_cast<void*>(w + lay[i].xtmp);
+      GroupedGemm& q = pr[i];
+      q = GroupedGemm{};
+      if (!tall) {  // [m, cols] = B[m, m] (K-major) x X[m(K), cols] (MN-major)
+        q.a_mn = false;
+        q.b_mn = true;
+        q.M = m;
+        q.N = g[i].cols;
+        q.K = m;
+        q.A = w + lay[i].b;
+        q.lda = m;
+        q.strideA = mm;
+        q.B = cur[i];
+        q.ldb = g[i].cols;
+        q.strideB = rc_;
+      } else {  // [rows, m] = X[rows, m(K)] (K-major) x B[m, m] (symmetric: K-major read of B^T = B)
+        q.a_mn = false;
+        q.b_mn = false;
+        q.M = g[i].rows;
+        q.N = m;
+        q.K = m;
+        q.A = cur[i];
+        q.lda = g[i].cols;
+        q.strideA = rc_;
+        q.B = w + lay[i].b;
+        q.ldb = m;
+        q.strideB = mm;
+      }
+      q.batch = g[i].batch;
+      q.C = cur[i];
+      q.ldc = g[i].cols;
+      q.strideC = rc_;
+      q.D = nxt;
+      q.ldd = g[i].cols;
+      q.strideD = rc_;
+      q.alpha = 1.0f;
+      q.beta = a;
+      q.alpha_vec = first ? g[i].inv_norm : nullptr;
+      q.beta_vec = first ? g[i].inv_norm : nullptr;
+      q.k_splits = 1;
+      if (last && g[i].n_peers > 0) {
+        q.peer_D = g[i].peer_out;
+        q.n_peers = g[i].n_peers;
+      }
+      cur[i] = nxt;
+    }
+    rc = gemm_grouped_2cta(pr, n, stream);
+    if (rc) return rc;
   }
   return B200_OK;
 }

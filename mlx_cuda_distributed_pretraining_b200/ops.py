@@ -202,6 +202,39 @@ def zeropower_via_newtonschulz5(g: torch.Tensor, steps: int = 5, eps: float = NS
     return x_out[0] if squeeze else x_out
 
 
+def zeropower_groups(gs: Sequence[torch.Tensor], steps: int = 5, eps: float = NS_EPS,
+                     coeffs: Sequence[float] = NS_COEFFS):
+    """Newton-Schulz of several [batch, rows, cols] groups (different shapes) through the whole-model chain:
+    every stage of the iteration is ONE grouped launch over all groups (b200_newton_schulz_multi).
+    Returns a list of bf16 tensors shaped like the inputs."""
+    import ctypes
+    from ._lib import NsGroup
+    require_device()
+    if not 1 <= len(gs) <= 6:
+        raise ValueError("zeropower_groups takes 1..6 groups")
+    keep, arr, outs = [], (NsGroup * len(gs))(), []
+    for i, g in enumerate(gs):
+        g3 = g.contiguous()
+        if g3.dim() != 3:
+            raise ValueError("each group must be [batch, rows, cols]")
+        x_in = g3 if g3.dtype == torch.bfloat16 else g3.to(torch.bfloat16)
+        inv, inv2 = ns_scales(sumsq(g3), eps)
+        x_out = torch.empty_like(x_in)
+        keep += [x_in, inv, inv2]
+        outs.append(x_out)
+        e = arr[i]
+        e.x_in, e.x_out = x_in.data_ptr(), x_out.data_ptr()
+        e.batch, e.rows, e.cols = x_in.shape
+        e.inv_norm, e.inv_norm_sq = inv.data_ptr(), inv2.data_ptr()
+        e.peer_out, e.n_peers = None, 0
+    a, b, c = coeffs
+    need = int(lib().b200_newton_schulz_multi_workspace_bytes(arr, len(gs), steps))
+    ws = torch.empty(max(need, 256), device=gs[0].device, dtype=torch.uint8)
+    check(lib().b200_newton_schulz_multi(arr, len(gs), steps, float(a), float(b), float(c), ws.data_ptr(),
+                                         ws.numel(), _stream()), "b200_newton_schulz_multi")
+    return outs
+
+
 def muon_momentum(g: torch.Tensor, buf: torch.Tensor, u: torch.Tensor, sumsq_out: torch.Tensor,
                   mu: float, nesterov: bool, gscale: float = 1.0) -> None:
     """g,buf,u: [batch, rows, cols] (g bf16|fp32, buf fp32, u bf16); sumsq_out fp32 [batch]."""

@@ -33,6 +33,7 @@ from typing import Callable, Dict, Optional, Tuple, Union
 import torch
 
 from .. import ops
+from .._lib import NsGroup
 from ..distributed import dp
 from ..flat import ParamStore, get_store
 
@@ -92,19 +93,24 @@ class Muon:
         self._store = store
         dev = store.device
         self._buf = torch.zeros(store.total, dtype=torch.float32, device=dev)  # momentum buffers
-        max_numel = max((g.numel for g in store.mat_groups), default=0)
-        max_batch = max((g.batch for g in store.mat_groups), default=1)
-        ws_bytes = max((ops.ns_workspace_bytes(g.batch, g.rows, g.cols, self.ns_steps)
-                        for g in store.mat_groups), default=0)
-        self._u = torch.empty(max(max_numel, 8), dtype=torch.bfloat16, device=dev)
-        self._x = torch.empty(max(max_numel, 8), dtype=torch.bfloat16, device=dev)
+        n_mat = max(store.mat_end, 8)
+        total_batch = max(sum(g.batch for g in store.mat_groups), 1)
+        # u = Nesterov momentum (Newton-Schulz input) and x = its orthogonalisation, for ALL shape groups at once
+        # (same flat layout as the parameters): the groups advance through the chain together, see update()
+        self._u = torch.empty(n_mat, dtype=torch.bfloat16, device=dev)
+        self._x = torch.empty(n_mat, dtype=torch.bfloat16, device=dev)
         self._xg = None  # per-group gather buffers of the sharded mode (allocated on first use)
         self._xg_handles = None  # symmetric-memory handles when the buffers are peer-mapped
         self._use_multicast = False
-        self._ws = torch.empty(max(ws_bytes, 256), dtype=torch.uint8, device=dev)
-        self._ss = torch.empty(max_batch, dtype=torch.float32, device=dev)
-        self._inv = torch.empty(max_batch, dtype=torch.float32, device=dev)
-        self._inv2 = torch.empty(max_batch, dtype=torch.float32, device=dev)
+        self._ws = torch.empty(256, dtype=torch.uint8, device=dev)   # grown on demand (update())
+        self._ss = torch.empty(total_batch, dtype=torch.float32, device=dev)
+        self._inv = torch.empty(total_batch, dtype=torch.float32, device=dev)
+        self._inv2 = torch.empty(total_batch, dtype=torch.float32, device=dev)
+        self._boff = []   # first matrix index of every group inside _ss / _inv / _inv2
+        o = 0
+        for g in store.mat_groups:
+            self._boff.append(o)
+            o += g.batch
         self.state = {}
         for g in store.mat_groups:
             for n in g.names:
@@ -132,76 +138,83 @@ class Muon:
         if world > 1 and self._xg is None:
             self._alloc_gather_buffers(store, world)
         p2p = world > 1 and self._xg_handles is not None and self._exchange != "nccl"
-        pending = []
-        # experimental (B200_NS_STREAMS=2, single process): run the shape groups' chains alternately on two
-        # side streams so that one group's tail wave is filled by the other group's tiles
-        n_streams = int(os.environ.get("B200_NS_STREAMS", "1")) if world == 1 else 1
-        if n_streams > 1:
-            self._update_multistream(store, gsrc, lr, lib, a, b, c, n_streams)
-            self._update_vectors(store, gsrc, lr)
-            self.count += 1
-            return
-        for gi, g in enumerate(store.mat_groups):
-            n = g.numel
-            rc = g.rows * g.cols
-            gg = gsrc[g.offset:g.offset + n]
-            buf = self._buf[g.offset:g.offset + n]
-            u = self._u[:n]
-            x = self._x[:n] if world == 1 else self._xg[gi]
-            rws = ops.reduce_workspace(store.device, g.batch)
-            ops.check(lib.b200_muon_momentum(gg.data_ptr(), ops._is_bf16(gg, "grad"), buf.data_ptr(),
-                                             u.data_ptr(), self._ss.data_ptr(), rc, g.batch,
-                                             float(self.momentum), int(self.nesterov),
-                                             float(self.grad_scale), rws.data_ptr(), rws.numel(), stream),
-                      "b200_muon_momentum")
+        groups = store.mat_groups
+        if groups:
+            # 1. momentum + Nesterov + per-matrix sum of squares for every group (muon.py:101,105), then ONE launch
+            #    turns all sums of squares into 1/(||u||+eps) and its square (muon.py:72-73)
+            for gi, g in enumerate(groups):
+                n, rc = g.numel, g.rows * g.cols
+                gg = gsrc[g.offset:g.offset + n]
+                rws = ops.reduce_workspace(store.device, g.batch)
+                ops.check(lib.b200_muon_momentum(gg.data_ptr(), ops._is_bf16(gg, "grad"),
+                                                 self._buf.data_ptr() + 4 * g.offset, self._u.data_ptr() + 2 * g.offset,
+                                                 self._ss.data_ptr() + 4 * self._boff[gi], rc, g.batch,
+                                                 float(self.momentum), int(self.nesterov), float(self.grad_scale),
+                                                 rws.data_ptr(), rws.numel(), stream), "b200_muon_momentum")
             ops.check(lib.b200_ns_scales(self._ss.data_ptr(), self._inv.data_ptr(), self._inv2.data_ptr(),
-                                         g.batch, ops.NS_EPS, stream), "b200_ns_scales")
-            mine = self.owned_ranges_of(gi, world, rank)   # matrices this rank orthogonalises
-            chunk = dp.chunk_ranges(g.batch, world)[0]
+                                         self._ss.numel(), ops.NS_EPS, stream), "b200_ns_scales")
+            # 2. Newton-Schulz on the matrices this rank owns, all groups advancing together: every stage of the
+            #    iteration is one grouped tcgen05 launch (b200_newton_schulz_multi)
+            entries, keep = [], []
+            for gi, g in enumerate(groups):
+                rc = g.rows * g.cols
+                xbase = self._x.data_ptr() + 2 * g.offset if world == 1 else self._xg[gi].data_ptr()
+                for lo, hi in self.owned_ranges_of(gi, world, rank):
+                    if hi <= lo:
+                        continue
+                    peers, n_peers = None, 0
+                    if p2p:   # GEMM -> all-gather in one kernel: the last GEMM stores into every rank's buffer
+                        hdl = self._xg_handles[gi]
+                        if self._use_multicast:
+                            # one store to the NVSwitch multicast address reaches every rank's replica: per-rank
+                            # NVLink egress is its own share, not (world - 1) copies of it
+                            ptrs = [int(hdl.multicast_ptr) + 2 * lo * rc]
+                        else:
+                            ptrs = [int(bp) + 2 * lo * rc for r, bp in enumerate(hdl.buffer_ptrs) if r != rank]
+                        peers = (ctypes.c_void_p * len(ptrs))(*ptrs)
+                        keep.append(peers)
+                        n_peers = len(ptrs)
+                    e = NsGroup()
+                    e.x_in = self._u.data_ptr() + 2 * (g.offset + lo * rc)
+                    e.x_out = xbase + 2 * lo * rc
+                    e.batch, e.rows, e.cols = hi - lo, g.rows, g.cols
+                    e.inv_norm = self._inv.data_ptr() + 4 * (self._boff[gi] + lo)
+                    e.inv_norm_sq = self._inv2.data_ptr() + 4 * (self._boff[gi] + lo)
+                    e.peer_out = ctypes.cast(peers, ctypes.POINTER(ctypes.c_void_p)) if peers is not None else None
+                    e.n_peers = n_peers
+                    entries.append(e)
             tok = ops._t0("newton_schulz")
-            for lo, hi in mine:
-                if hi <= lo:
-                    continue
-                if p2p:   # GEMM -> all-gather in one kernel: the last GEMM stores into every rank's buffer
-                    hdl = self._xg_handles[gi]
-                    if self._use_multicast:
-                        # one store to the NVSwitch multicast address reaches every rank's replica: per-rank
-                        # NVLink egress is its own share, not (world - 1) copies of it
-                        ptrs = [int(hdl.multicast_ptr) + 2 * lo * rc]
-                    else:
-                        ptrs = [int(bp) + 2 * lo * rc for r, bp in enumerate(hdl.buffer_ptrs) if r != rank]
-                    peers = (ctypes.c_void_p * len(ptrs))(*ptrs)
-                    ops.check(lib.b200_newton_schulz_allgather(
-                        u.data_ptr() + 2 * lo * rc, x.data_ptr() + 2 * lo * rc, hi - lo, g.rows, g.cols,
-                        self.ns_steps, a, b, c, self._inv.data_ptr() + 4 * lo, self._inv2.data_ptr() + 4 * lo,
-                        self._ws.data_ptr(), self._ws.numel(), peers, len(ptrs), stream),
-                        "b200_newton_schulz_allgather")
-                    continue
-                ops.check(lib.b200_newton_schulz(u.data_ptr() + 2 * lo * rc, x.data_ptr() + 2 * lo * rc, hi - lo,
-                                                 g.rows, g.cols, self.ns_steps, a, b, c,
-                                                 self._inv.data_ptr() + 4 * lo, self._inv2.data_ptr() + 4 * lo,
-                                                 self._ws.data_ptr(), self._ws.numel(), stream),
-                          "b200_newton_schulz")
+            for i in range(0, len(entries), 6):   # one grouped launch takes up to 6 problems
+                chunk = entries[i:i + 6]
+                arr = (NsGroup * len(chunk))(*chunk)
+                need = int(lib.b200_newton_schulz_multi_workspace_bytes(arr, len(chunk), self.ns_steps))
+                if self._ws.numel() < need:
+                    self._ws = torch.empty(need, dtype=torch.uint8, device=store.device)
+                ops.check(lib.b200_newton_schulz_multi(arr, len(chunk), self.ns_steps, a, b, c, self._ws.data_ptr(),
+                                                       self._ws.numel(), stream), "b200_newton_schulz_multi")
             ops._t1(tok)
-            works = []
-            if world > 1 and not p2p:
-                if g.batch >= world:
-                    works.append(dp.all_gather_chunks_(x, chunk * rc, async_op=True))
-                else:
-                    works += [dp.broadcast_async_(x[i * rc:(i + 1) * rc], dp.small_group_owner(i, world))
-                              for i in range(g.batch)]
-            pending.append((g, x, works))
-            if world == 1:
-                self._apply(store, g, x, lr, lib, stream)   # the single x buffer is reused by the next group
-                pending.pop()
-        if p2p:
-            # every rank's peer stores are stream-ordered before its barrier arrival
-            self._xg_handles[0].barrier()
-        for g, x, works in pending:
-            for w in works:
-                if w is not None:
-                    w.wait()   # orders the current stream after the collective
-            self._apply(store, g, x, lr, lib, stream)
+            # 3. exchange (data parallel) and apply
+            pending = []
+            for gi, g in enumerate(groups):
+                rc = g.rows * g.cols
+                x = self._x[g.offset:g.offset + g.numel] if world == 1 else self._xg[gi]
+                works = []
+                if world > 1 and not p2p:
+                    chunk_len = dp.chunk_ranges(g.batch, world)[0]
+                    if g.batch >= world:
+                        works.append(dp.all_gather_chunks_(x, chunk_len * rc, async_op=True))
+                    else:
+                        works += [dp.broadcast_async_(x[i * rc:(i + 1) * rc], dp.small_group_owner(i, world))
+                                  for i in range(g.batch)]
+                pending.append((g, x, works))
+            if p2p:
+                # every rank's peer stores are stream-ordered before its barrier arrival
+                self._xg_handles[0].barrier()
+            for g, x, works in pending:
+                for wk in works:
+                    if wk is not None:
+                        wk.wait()   # orders the current stream after the collective
+                self._apply(store, g, x, lr, lib, stream)
         self._update_vectors(store, gsrc, lr)
         self.count += 1
 
@@ -214,42 +227,6 @@ class Muon:
                 p16 = store.shadow[lo:hi] if store.mixed else None
                 ops.sgd_momentum(store.master[lo:hi], p16, gsrc[lo:hi], self._buf[lo:hi], self.momentum,
                                  self.nesterov, lr, self.grad_scale)
-
-    def _update_multistream(self, store, gsrc, lr, lib, a, b, c, n_streams: int) -> None:
-        main = torch.cuda.current_stream()
-        if getattr(self, "_side", None) is None or len(self._side) != n_streams:
-            self._side = [torch.cuda.Stream(device=store.device) for _ in range(n_streams)]
-            self._side_bufs = [tuple(torch.empty_like(t) for t in (self._u, self._x, self._ws, self._ss, self._inv, self._inv2))
-                               for _ in range(n_streams)]
-        fork = torch.cuda.Event()
-        fork.record(main)
-        tok = ops._t0("newton_schulz")   # spans the whole forked region on the main stream
-        for st in self._side:
-            st.wait_event(fork)
-        for gi, g in enumerate(store.mat_groups):
-            st = self._side[gi % n_streams]
-            u_, x_, ws_, ss_, inv_, inv2_ = self._side_bufs[gi % n_streams]
-            n, rc = g.numel, g.rows * g.cols
-            gg = gsrc[g.offset:g.offset + n]
-            buf = self._buf[g.offset:g.offset + n]
-            with torch.cuda.stream(st):
-                sp = ops._stream()
-                rws = ops.reduce_workspace(store.device, g.batch)   # keyed by stream: one per side stream
-                ops.check(lib.b200_muon_momentum(gg.data_ptr(), ops._is_bf16(gg, "grad"), buf.data_ptr(), u_.data_ptr(),
-                                                 ss_.data_ptr(), rc, g.batch, float(self.momentum), int(self.nesterov),
-                                                 float(self.grad_scale), rws.data_ptr(), rws.numel(), sp),
-                          "b200_muon_momentum")
-                ops.check(lib.b200_ns_scales(ss_.data_ptr(), inv_.data_ptr(), inv2_.data_ptr(), g.batch, ops.NS_EPS, sp),
-                          "b200_ns_scales")
-                ops.check(lib.b200_newton_schulz(u_.data_ptr(), x_.data_ptr(), g.batch, g.rows, g.cols, self.ns_steps,
-                                                 a, b, c, inv_.data_ptr(), inv2_.data_ptr(), ws_.data_ptr(), ws_.numel(),
-                                                 sp), "b200_newton_schulz")
-                self._apply(store, g, x_, lr, lib, sp)
-        for st in self._side:
-            ev = torch.cuda.Event()
-            ev.record(st)
-            main.wait_event(ev)
-        ops._t1(tok)
 
     def _alloc_gather_buffers(self, store, world: int) -> None:
         """One padded buffer per shape group: world * ceil(batch/world) matrices, so exchanges can stay in

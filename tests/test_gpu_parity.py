@@ -681,3 +681,23 @@ def test_newton_schulz_c5_shapes(ops, shape):
     g = torch.randn(*shape) * 0.02
     x = ops.zeropower_via_newtonschulz5(g.cuda())
     assert rel(x, R.newton_schulz5(g)) < 3e-2
+
+
+def test_newton_schulz_grouped_chain_matches_per_group(ops):
+    """b200_newton_schulz_multi (one grouped launch per stage over all shape groups, run-time operand layouts,
+    in-launch split-K of a lone tall matrix) against the per-group chain and the oracle: wide, tall, square and a
+    split-K group in the same launch.  Same tiles, same accumulation order -> bit-identical to the per-group
+    kernels wherever the split-K choice is the same."""
+    torch.manual_seed(60)
+    shapes = [(3, 256, 512), (2, 768, 256), (2, 512, 512), (1, 5000, 512), (4, 384, 1024)]
+    gs = [(torch.randn(*s) * 0.02).cuda() for s in shapes]
+    outs = ops.zeropower_groups(gs)
+    for g, x, s in zip(gs, outs, shapes):
+        single = ops.zeropower_via_newtonschulz5(g)
+        assert rel(x, single) < 2e-3, s
+        assert rel(x, R.newton_schulz5(g.cpu().double())) < 3e-2, s
+    assert torch.equal(outs[0], ops.zeropower_via_newtonschulz5(gs[0]))     # no split-K involved: same bits
+    # groups too small for the CTA-pair kernel take the per-group fallback inside the same entry point
+    small = [(torch.randn(2, 64, 136) * 0.1).cuda(), (torch.randn(1, 136, 72) * 0.1).cuda()]
+    for g, x in zip(small, ops.zeropower_groups(small)):
+        assert torch.equal(x, ops.zeropower_via_newtonschulz5(g))
