@@ -400,6 +400,25 @@ def run_workload(tag: str, K: int, W: int, with_e2e: bool = True, with_dp_check:
         torch.distributed.all_reduce(hi, op=torch.distributed.ReduceOp.MAX)
         dp_check = {"replicas_bit_identical": bool(int(lo.item()) == int(hi.item())),
                     "after_updates": 2 * K + W + 1, "exchange_in_timed_region": getattr(tr.optimizer, "exchange_mode", None)}
+        # gradient exchange precision: the flat gradient buffer is reduced in its storage type (bf16 unless the
+        # config accumulates micro-batches in fp32); measure what that costs against an fp32 reduction of the same
+        # per-rank gradients (the reference averages fp32 arrays, hybrid_distributed.py:352)
+        if not tr.use_acc and tr.store.grad.dtype == torch.bfloat16:
+            tr.store.zero_grad()
+            fb = tr.data_manager.generate_batch(10 ** 6 + 7).to(dev)
+            l_, _ = tr.compute_loss(tr.model, fb[:, :-1], fb[:, 1:])
+            l_.backward()
+            g32 = tr.store.grad.float()
+            g16 = tr.store.grad.clone()
+            torch.distributed.all_reduce(g32)
+            torch.distributed.all_reduce(g16)
+            dp_check["grad_allreduce"] = {"dtype": "bf16", "ranks": world,
+                                          "rel_err_vs_fp32_reduce": float((g16.float() - g32).norm() / (g32.norm() + 1e-30)),
+                                          "bf16_storage_rounding_alone": float((g32.to(torch.bfloat16).float() - g32).norm() / (g32.norm() + 1e-30))}
+            del g32, g16
+            tr.store.zero_grad()
+        elif tr.use_acc:
+            dp_check["grad_allreduce"] = {"dtype": "f32", "ranks": world, "note": "fp32 accumulation buffer is reduced"}
         opt = getattr(tr.optimizer, "matrix_optimizer", tr.optimizer)
         if hasattr(opt, "set_exchange") and getattr(opt, "shard_ns", False):
             # ONE update from identical state through every exchange implementation: the fused GEMM -> all-gather
@@ -514,6 +533,7 @@ def main() -> None:
     ap.add_argument("--config", type=str, default="c2", choices=sorted(CONFIG_FILES))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-configs-block", action="store_true", help="skip the extra C3 single-GPU leg of the default run")
+    ap.add_argument("--no-e2e", action="store_true", help="profiling runs: only the device-resident leg")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -525,7 +545,7 @@ def main() -> None:
     if world != args.gpus and world > 1:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
     tag = args.config
-    r = run_workload(tag, args.steps, args.warmup)
+    r = run_workload(tag, args.steps, args.warmup, with_e2e=not args.no_e2e)
     extra = None
     if world == 1 and tag == "c2" and not args.no_configs_block:
         extra = run_workload("c3", max(2, min(args.steps, 4)), 3, with_e2e=False)

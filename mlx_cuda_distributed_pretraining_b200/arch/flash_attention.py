@@ -57,7 +57,11 @@ class FlashAttention(nn.Module):
                 "the fused kernel supports mask=None or the causal mask (CausalMask); "
                 "arbitrary additive masks are outside the reference's training path")
         dt = q.dtype
-        if dt != torch.bfloat16:  # tensor cores run bf16 operands with fp32 accumulation
+        if dt == torch.float32 and 3 * self.head_dim <= 128:
+            # full-precision configs (mixed_precision: false, e.g. BASELINE C1, head_dim 16): logits through
+            # three-term bf16 products (hi/lo split operands), ~fp32-accurate scores on the same kernels
+            return ops.attention_fp32(q, k, v, self.scale, causal)
+        if dt != torch.bfloat16:  # larger head dims: bf16 operands with fp32 accumulation (stated in DESIGN.md)
             q, k, v = q.to(torch.bfloat16), k.to(torch.bfloat16), v.to(torch.bfloat16)
         o = ops.attention(q, k, v, self.scale, causal)
         return o if dt == torch.bfloat16 else o.to(dt)

@@ -224,18 +224,39 @@ class TokenizerManager:
 
 
 class SyntheticData:
-    """SURVEY 8d synthetic token stream; same draws for the CUDA path and the CPU oracle."""
+    """SURVEY 8d synthetic token stream; same draws for the CUDA path and the CPU oracle.
 
-    def __init__(self, vocab: int, batch_size: int, seq_len: int, rank: int = 0, num_batches: int = 1 << 30):
+    `data.input_file: synthetic`         uniform tokens (BASELINE configs), optimum loss = ln(vocab)
+    `data.input_file: synthetic:markov`  a fixed first-order Markov chain (4 successors per token, 10 % uniform
+                                         noise): LEARNABLE, so a loss curve can tell two optimizers apart; the
+                                         oracle's twin is reference_math.synthetic_batch_markov (same draws)."""
+
+    def __init__(self, vocab: int, batch_size: int, seq_len: int, rank: int = 0, num_batches: int = 1 << 30,
+                 kind: str = "uniform"):
         self.vocab, self.batch_size, self.seq_len, self.rank = vocab, batch_size, seq_len, rank
         self.train_docs = range(num_batches * batch_size)
         self.has_validation_data = False
         self.num_validation_batches = 0
         self.val_ptr = 0
+        self.kind = kind
+        if kind not in ("uniform", "markov"):
+            raise ValueError(f"unknown synthetic data kind {kind!r} (uniform | markov)")
+        self._succ = (torch.randint(0, vocab, (vocab, 4), generator=torch.Generator().manual_seed(4242), dtype=torch.int64)
+                      if kind == "markov" else None)
 
     def generate_batch(self, step: int) -> torch.Tensor:
         g = torch.Generator().manual_seed(42 + 1000 * step + self.rank)
-        return torch.randint(0, self.vocab, (self.batch_size, self.seq_len + 1), generator=g, dtype=torch.int64)
+        B, S = self.batch_size, self.seq_len
+        if self.kind == "uniform":
+            return torch.randint(0, self.vocab, (B, S + 1), generator=g, dtype=torch.int64)
+        out = torch.empty((B, S + 1), dtype=torch.int64)
+        out[:, 0] = torch.randint(0, self.vocab, (B,), generator=g, dtype=torch.int64)
+        choice = torch.randint(0, 4, (B, S), generator=g, dtype=torch.int64)
+        noisy = torch.rand((B, S), generator=g) < 0.1
+        rnd = torch.randint(0, self.vocab, (B, S), generator=g, dtype=torch.int64)
+        for t in range(S):
+            out[:, t + 1] = torch.where(noisy[:, t], rnd[:, t], self._succ[out[:, t], choice[:, t]])
+        return out
 
 
 class DataManager:
@@ -547,8 +568,9 @@ class Trainer:
         bs = hp["batch_size"]
         seq = self.config.data.preprocessing["max_context_size"]
         if self.synthetic:
+            kind = self.config.data.input_file.split(":", 1)[1] if ":" in self.config.data.input_file else "uniform"
             self.data_manager = SyntheticData(self.config.data.tokenizer["normal_vocab_size"], bs, seq, self.rank,
-                                              num_batches=hp.get("iters", 1000))
+                                              num_batches=hp.get("iters", 1000), kind=kind)
         else:
             self.data_manager = DataManager(self.config.data, self.tokenizer, bs, self.rank, self.world)
 

@@ -585,6 +585,64 @@ class _AttentionFn(torch.autograd.Function):
         return dq, dk, dv, None, None
 
 
+def _hi_lo(x: torch.Tensor):
+    hi = x.to(torch.bfloat16)
+    return hi, (x - hi.float()).to(torch.bfloat16)
+
+
+class _AttentionX3Fn(torch.autograd.Function):
+    """fp32 attention on the bf16 tensor-core kernels for small head dims (3*D <= 128), used when the config asks
+    for full precision (`mixed_precision: false`, e.g. BASELINE C1 with D = 16).  Each fp32 operand x = hi + lo
+    (two bf16) is laid along the head dimension so that ONE bf16 kernel call evaluates the three-term products:
+
+        Q' = [qh | ql | qh]   K' = [kh | kh | kl]   ->  Q'K'^T = qh kh + ql kh + qh kl  ~=  q k^T   (~16 bits)
+        V' = [vh | vh | vl]                         ->  O' = [P vh | P vh | P vl],  o = O'[0:D] + O'[2D:3D]
+        dO' = [gh | gl | gh]  ->  dP = gh vh + gl vh + gh vl ;  dq = dQ'[0:D] + dQ'[2D:3D],
+                                  dk = dK'[0:D] + dK'[D:2D],    dv = dV'[0:D] + dV'[D:2D]
+
+    The logits (where bf16 operand rounding hurts most: an error of |s| * 2^-9 in the exponent) are thus computed
+    to fp32-like accuracy; P and the kernel outputs still pass through one bf16 rounding each."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, scale, causal):
+        D = q.shape[-1]
+        Dp = _pad_head_dim(3 * D)
+        (qh, ql), (kh, kl), (vh, vl) = _hi_lo(q), _hi_lo(k), _hi_lo(v)
+
+        def cat3(a, b, c):
+            t = torch.cat([a, b, c], dim=-1)
+            return (torch.nn.functional.pad(t, (0, Dp - 3 * D)) if Dp != 3 * D else t).contiguous()
+        q3, k3, v3 = cat3(qh, ql, qh), cat3(kh, kh, kl), cat3(vh, vh, vl)
+        o3, lse = attention_fwd_raw(q3, k3, v3, scale, causal)
+        ctx.save_for_backward(q3, k3, v3, o3, lse)
+        ctx.scale, ctx.causal, ctx.D, ctx.Dp = scale, causal, D, Dp
+        return o3[..., :D].float() + o3[..., 2 * D:3 * D].float()
+
+    @staticmethod
+    def backward(ctx, do):
+        q3, k3, v3, o3, lse = ctx.saved_tensors
+        D, Dp = ctx.D, ctx.Dp
+        gh, gl = _hi_lo(do.float())
+        g3 = torch.cat([gh, gl, gh], dim=-1)
+        if Dp != 3 * D:
+            g3 = torch.nn.functional.pad(g3, (0, Dp - 3 * D))
+        dq3, dk3, dv3 = attention_bwd_raw(q3, k3, v3, o3, g3.contiguous(), lse, ctx.scale, ctx.causal)
+        dq = dq3[..., :D].float() + dq3[..., 2 * D:3 * D].float()
+        dk = dk3[..., :D].float() + dk3[..., D:2 * D].float()
+        dv = dv3[..., :D].float() + dv3[..., D:2 * D].float()
+        return dq, dk, dv, None, None
+
+
+def attention_fp32(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, scale: Optional[float] = None,
+                   causal: bool = True) -> torch.Tensor:
+    """fp32 in / fp32 out attention with bf16x3 logits (see _AttentionX3Fn); head_dim <= 42."""
+    if 3 * q.shape[-1] > 128:
+        raise ValueError("attention_fp32: head_dim must be <= 42 (three bf16 copies must fit a 128-wide tile)")
+    if scale is None:
+        scale = q.shape[-1] ** -0.5
+    return _AttentionX3Fn.apply(q.float(), k.float(), v.float(), float(scale), bool(causal))
+
+
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, scale: Optional[float] = None,
               causal: bool = True) -> torch.Tensor:
     """softmax(q k^T * scale + causal_mask) v with GQA head sharing; [B,S,H,D] layout, bf16."""

@@ -701,3 +701,26 @@ def test_newton_schulz_grouped_chain_matches_per_group(ops):
     small = [(torch.randn(2, 64, 136) * 0.1).cuda(), (torch.randn(1, 136, 72) * 0.1).cuda()]
     for g, x in zip(small, ops.zeropower_groups(small)):
         assert torch.equal(x, ops.zeropower_via_newtonschulz5(g))
+
+
+@pytest.mark.parametrize("B,S,H,Hk,D", [(2, 256, 8, 8, 16), (1, 200, 4, 2, 32), (2, 130, 4, 4, 40)])
+def test_attention_fp32_path_large_logits(ops, B, S, H, Hk, D):
+    """Full-precision configs (mixed_precision: false; BASELINE C1 has head_dim 16): bf16x3 logits.  With LARGE
+    scores (|s| ~ 40, the regime a 2e-2-lr AdamW run reaches) plain bf16 operands put an error of |s| * 2^-9 in
+    the exponent; the three-term path must stay at the bf16-OUTPUT rounding level, several times better."""
+    torch.manual_seed(70 + D)
+    q = (torch.randn(B, S, H, D, device="cuda") * 4).requires_grad_(True)
+    k = (torch.randn(B, S, Hk, D, device="cuda") * 4).requires_grad_(True)
+    v = torch.randn(B, S, Hk, D, device="cuda").requires_grad_(True)
+    do = torch.randn(B, S, H, D, device="cuda")
+    o = ops.attention_fp32(q, k, v, D ** -0.5, True)
+    o.backward(do)
+    qr, kr, vr = (t.detach().double().cpu().requires_grad_(True) for t in (q, k, v))
+    orf = R.attention(qr, kr, vr, D ** -0.5, R.causal_mask(S, dtype=torch.float64))
+    orf.backward(do.double().cpu())
+    errs = (rel(o, orf), rel(q.grad, qr.grad), rel(k.grad, kr.grad), rel(v.grad, vr.grad))
+    assert max(errs) < 8e-3, errs
+    # the plain bf16-operand path on the same inputs, for the record: must be clearly worse on the logits side
+    qb, kb, vb = (t.detach().to(torch.bfloat16).requires_grad_(True) for t in (q, k, v))
+    ob = ops.attention(qb, kb, vb, D ** -0.5, True)
+    assert rel(ob, orf) > 2 * errs[0], (rel(ob, orf), errs[0])

@@ -327,3 +327,48 @@ def test_explicit_batch_path_never_reuses_a_pinned_buffer_in_flight(tmp_path):
         devs.append(tr._to_device(b))
     torch.cuda.synchronize()
     assert all(torch.equal(d.cpu(), b) for d, b in zip(devs, batches))
+
+
+@pytest.mark.parametrize("data", ["uniform", "markov"])
+def test_c1_loss_curve_matches_oracle(tmp_path, data):
+    """BASELINE configs[0]: Llama 2M + AdamW (configs/c1-llama2m-adamw.yaml), fp32 config, "1k iters synthetic
+    tokens ... plumbing + loss parity".  The product Trainer runs the whole schedule on the GPU; the oracle's curve
+    (CPU fp32, tests/golden/make_c1_curve.py, ~80 min on 8 cores, committed as tests/golden/c1_curve_*.json) is
+    compared step by step.  `uniform` = the BASELINE token stream (optimum ln 256, the curve is a fast decay onto a
+    plateau); `markov` = a learnable stream (the curve keeps falling, so it separates optimizers).
+    Tolerance (1e-2 absolute): max |loss_gpu - loss_oracle| over all steps; the measured value is
+    written to gpurun_out/c1_curve_<data>.json for the record."""
+    import yaml
+    from mlx_cuda_distributed_pretraining_b200.core.training import Config, Trainer
+    fx = ROOT / "tests" / "golden" / f"c1_curve_{data}.json"
+    if not fx.exists():
+        pytest.skip(f"{fx.name} not generated yet")
+    ref = json.loads(fx.read_text())
+    d = yaml.safe_load((ROOT / "configs" / "c1-llama2m-adamw.yaml").read_text())
+    d["name"] = f"c1-curve-{data}"
+    d["data"]["input_file"] = "synthetic" if data == "uniform" else "synthetic:markov"
+    d["training"]["hyperparameters"]["iters"] = ref["total_steps"]
+    d["logging"]["steps"] = {"logging_interval": 10 ** 9, "checkpoint_interval": 0, "validation_interval": 0}
+    tr = Trainer(Config.from_dict(d), synthetic=True, quiet=True, run_root=str(tmp_path))
+    tr._accum_step, tr._accum_tokens = 0, 0
+    n = min(ref["steps"], len(ref["loss"]))
+    losses = []
+    for step in range(n):
+        loss, _, _ = tr.train_step(step, tr.data_manager.generate_batch(step))
+        losses.append(loss)
+    got = torch.stack(losses).float().cpu()
+    want = torch.tensor(ref["loss"][:n])
+    diff = (got - want).abs()
+    out = ROOT / "gpurun_out"
+    out.mkdir(exist_ok=True)
+    (out / f"c1_curve_{data}.json").write_text(json.dumps({
+        "steps": n, "max_abs_diff": float(diff.max()), "argmax": int(diff.argmax()), "mean_abs_diff": float(diff.mean()),
+        "final_gpu": float(got[-1]), "final_oracle": float(want[-1]), "first_gpu": float(got[0]),
+        "first_oracle": float(want[0]), "max_abs_diff_after_50": float(diff[50:].max()) if n > 50 else None,
+        "loss_gpu": [round(float(x), 5) for x in got]}))
+    assert torch.isfinite(got).all()
+    assert float(diff.max()) < C1_CURVE_TOL[data], (float(diff.max()), int(diff.argmax()))
+
+
+# measured on B200 (gpurun_out/c1_curve_*.json copied to profiles/): see DESIGN.md section 5
+C1_CURVE_TOL = {"uniform": 1e-2, "markov": 1e-2}

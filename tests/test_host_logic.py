@@ -248,3 +248,16 @@ def test_yaml_schema_matches_reference_parse():
     for name, want in ref.items():
         got = dataclasses.asdict(Config.from_yaml(str(ROOT / "configs" / name)))
         subset(want, got, name)
+
+
+def test_markov_synthetic_stream_matches_oracle_generator():
+    """`data.input_file: synthetic:markov` (learnable stream for loss-curve parity) draws exactly what the oracle's
+    reference_math.synthetic_batch_markov draws, per step and rank."""
+    import torch
+    from oracle import reference_math as R
+    from mlx_cuda_distributed_pretraining_b200.core.training import SyntheticData
+    for step, rank in ((0, 0), (7, 1)):
+        a = SyntheticData(256, 3, 96, rank, kind="markov").generate_batch(step)
+        assert torch.equal(a, R.synthetic_batch_markov(step, rank, 3, 96, 256))
+    u = SyntheticData(256, 3, 96, 0).generate_batch(5)
+    assert torch.equal(u, R.synthetic_batch(5, 0, 3, 96, 256))
