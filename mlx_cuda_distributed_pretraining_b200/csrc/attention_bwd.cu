@@ -374,11 +374,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   }
 }
 
-// delta[b,h,s] = sum_d o[b,s,h,d] * do[b,s,h,d]; LPR = D/8 lanes cooperate on one row
+// delta[b,h,s] = sum_d o[b,s,h,d] * do[b,s,h,d]; LPR = D/8 lanes cooperate on one row.  The same pass zeroes the
+// fp32 dQ accumulator (same [B,S,H,D] index space: each thread clears the 8 floats under the 8 bf16 it reads), so the
+// backward needs no separate memset launch over 4*B*S*H*D bytes.
 template <int D>
 __global__ void __launch_bounds__(256)
 attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ d_o,
-                  float* __restrict__ delta, int B, int S, int H) {
+                  float* __restrict__ delta, float* __restrict__ dq_acc, int B, int S, int H) {
   constexpr int LPR = D / 8;
   const long long rows = (long long)B * S * H;
   const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -388,6 +390,9 @@ attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __re
   if (r < rows) {
     const uint4 a = ldg128(o + r * D + sub * 8);
     const uint4 c = ldg128(d_o + r * D + sub * 8);
+    float4* z = reinterpret_cast<float4*>(dq_acc + r * D + sub * 8);
+    z[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+    z[1] = make_float4(0.f, 0.f, 0.f, 0.f);
     const uint32_t* au = &a.x;
     const uint32_t* cu = &c.x;
 #pragma unroll
@@ -467,14 +472,13 @@ int attn_bwd(const void* q, const void* k, const void* v, const void* o, const v
   float* dq_acc = reinterpret_cast<float*>(ws);
   float* delta = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + al256((size_t)B * S * H * D * 4));
   const long long n = (long long)B * S * H * D;
-  B200_CHECK_CUDA(cudaMemsetAsync(dq_acc, 0, (size_t)n * 4, stream));
   {
     const long long threads = (long long)B * S * H * (D / 8);
     const int blocks = (int)((threads + 255) / 256);
     if (D == 64)
-      attn_delta_kernel<64><<<blocks, 256, 0, stream>>>((const __nv_bfloat16*)o, (const __nv_bfloat16*)d_o, delta, B, S, H);
+      attn_delta_kernel<64><<<blocks, 256, 0, stream>>>((const __nv_bfloat16*)o, (const __nv_bfloat16*)d_o, delta, dq_acc, B, S, H);
     else
-      attn_delta_kernel<128><<<blocks, 256, 0, stream>>>((const __nv_bfloat16*)o, (const __nv_bfloat16*)d_o, delta, B, S, H);
+      attn_delta_kernel<128><<<blocks, 256, 0, stream>>>((const __nv_bfloat16*)o, (const __nv_bfloat16*)d_o, delta, dq_acc, B, S, H);
     B200_CHECK_LAUNCH();
   }
   CUtensorMap tmQ, tmK, tmV, tmDO;

@@ -15,6 +15,12 @@
 //     warpgroup sustains ~20 B/clk/SM this way (tools/microbench/red_pattern.cu: 1600 cycles per tile
 //     with all SMs active, 5.7 TB/s chip-wide, L2-resident accumulator), inside the softmax's 2400;
 //   * reads LSE / delta as 128-bit shared loads, prefetched one iteration ahead.
+// r02: the softmax is split into two phases so that it never waits for the tensor core with the SAME 512 TMEM
+// columns: phase A reads S^T and produces P^T (exp2; packed bf16 kept in registers and stored to TMEM for dV),
+// phase B reads dP^T and produces dS^T = P^T o (dP^T - delta).  S^T(it+1) is issued the moment phase A(it) has the
+// scores in registers (barrier s_free) -- it completes under phase B(it) -- and dP^T(it+1) is issued right after
+// phase B(it) (behind dV(it), which frees P^T) -- it completes under phase A(it+1).  The r01 version issued both
+// at the end of the softmax and the softmax threads idled ~1350 of every ~3600 cycles waiting for them.
 // Tried and dropped (r01 traces): computing S^T/dP^T in two 64-query halves so that half A of tile it+1
 // is issued mid-softmax -- the extra operand re-reads slowed the softmax's own shared-memory stores more
 // than the overlap gained.  Shared-memory bandwidth is the co-bottleneck here: MMA operand reads
@@ -76,10 +82,15 @@ __device__ __forceinline__ void red_add_v4(float* addr, float4 v) {
                "f"(v.w)
                : "memory");
 }
-__device__ __forceinline__ void st_tile_chunk(uint32_t tile, int row, int chunk, const float* f) {
+__device__ __forceinline__ uint32_t mul_bf16x2(uint32_t a, uint32_t b) {
+  uint32_t d;
+  asm volatile("mul.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+}
+// 8 packed bf16 (4 words) of key row `row`, query chunk `chunk`, into a K-major 128B-swizzled [128 x 128] tile
+__device__ __forceinline__ void st_tile_chunk_packed(uint32_t tile, int row, int chunk, const uint32_t* w) {
   const uint32_t addr = tile + (chunk >> 3) * 16384 + row * 128 + (((chunk & 7) ^ (row & 7)) << 4);
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pack_bf16x2(f[0], f[1])),
-               "r"(pack_bf16x2(f[2], f[3])), "r"(pack_bf16x2(f[4], f[5])), "r"(pack_bf16x2(f[6], f[7]))
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3])
                : "memory");
 }
 
@@ -102,7 +113,9 @@ attn_bwd64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   auto q_empty = [&](int s) { return bar + 8u * (19 + s); };
   const uint32_t pt_free = bar + 8u * 1;
   const uint32_t all_done = bar + 8u * 2;  // single phase: every MMA of this CTA retired
-  const uint32_t s_full = bar + 8u * 5;
+  const uint32_t s_full = bar + 8u * 5;   // S^T(it) complete
+  const uint32_t dp_full = bar + 8u * 3;  // dP^T(it) complete
+  const uint32_t s_free = bar + 8u * 4;   // phase A(it) has read S^T(it): S^T(it+1) may be issued
   const uint32_t pds_full = bar + 8u * 6;
   const uint32_t dq_full = bar + 8u * 7;
   const uint32_t dq_empty = bar + 8u * 8;
@@ -133,6 +146,8 @@ attn_bwd64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     mbar_init(pt_free, 1);
     mbar_init(all_done, 1);
     mbar_init(s_full, 1);
+    mbar_init(dp_full, 1);
+    mbar_init(s_free, 8);
     mbar_init(pds_full, 8);
     mbar_init(dq_full, 1);
     mbar_init(dq_empty, 4);
@@ -167,7 +182,7 @@ attn_bwd64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, false, false);  // K-major x K-major
     constexpr uint32_t idesc_kv = make_idesc_bf16(128, D, false, true);    // K-major x MN-major
     constexpr uint32_t idesc_dq = make_idesc_bf16(128, D, true, true);     // MN-major x MN-major
-    auto issue_s = [&](int it) {  // S^T = K Q^T, dP^T = V dO^T  (M = keys, N = queries, K = head dim)
+    auto issue_s = [&](int it) {  // S^T = K Q^T  (M = keys, N = queries, K = head dim)
       const int st = it % QS;
       mbar_wait(q_full(st), (it / QS) & 1u);
       tc_fence_after_sync();
@@ -176,34 +191,52 @@ attn_bwd64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         for (int kk = 0; kk < D / 16; ++kk)
           umma_bf16_ss(tmem_base + TM_S, make_smem_desc_sw128(sK + kk * 32, 0, 1024),
                        make_smem_desc_sw128(sQ(st) + kk * 32, 0, 1024), idesc_s, kk != 0);
-#pragma unroll
-        for (int kk = 0; kk < D / 16; ++kk)
-          umma_bf16_ss(tmem_base + TM_DP, make_smem_desc_sw128(sV + kk * 32, 0, 1024),
-                       make_smem_desc_sw128(sDO(st) + kk * 32, 0, 1024), idesc_s, kk != 0);
         umma_commit(s_full);
       }
       __syncwarp();
     };
+    auto issue_dp = [&](int it) {  // dP^T = V dO^T; the stage's q_full was already observed by issue_s(it)
+      const int st = it % QS;
+      if (elect_one()) {
+#pragma unroll
+        for (int kk = 0; kk < D / 16; ++kk)
+          umma_bf16_ss(tmem_base + TM_DP, make_smem_desc_sw128(sV + kk * 32, 0, 1024),
+                       make_smem_desc_sw128(sDO(st) + kk * 32, 0, 1024), idesc_s, kk != 0);
+        umma_commit(dp_full);
+      }
+      __syncwarp();
+    };
     mbar_wait(kv_full, 0);
-    if (n_it > 0) issue_s(0);
+    if (n_it > 0) {
+      issue_s(0);
+      issue_dp(0);
+    }
     for (int it = 0; it < n_it; ++it) {
       const int st = it % QS, bf = it & 1;
       if (lane == 0) T64(8);
-      mbar_wait(pds_full, it & 1u);  // softmax(it) done: S/dP columns free, P^T (TMEM) and dS^T[bf] written
+      if (it + 1 < n_it) {
+        mbar_wait(s_free, it & 1u);  // phase A(it) holds the scores in registers: S^T columns are free
+        tc_fence_after_sync();
+        issue_s(it + 1);             // completes while phase B(it) runs
+      }
       if (lane == 0) T64(9);
-      if (it + 1 < n_it) issue_s(it + 1);
+      mbar_wait(pds_full, it & 1u);  // phase B(it) done: dP^T columns free, P^T (TMEM) and dS^T[bf] written
       if (lane == 0) T64(10);
       if (it > 0) mbar_wait(dq_empty, (it - 1) & 1u);  // dQ(it-1) copied out of TMEM by the drain warps
       tc_fence_after_sync();
       if (lane == 0) T64(11);
       if (elect_one()) {
         // dV += P^T dO  (M = keys, N = head dim, K = queries): A = P^T straight from TMEM, 8 packed columns
-        // per K step; then P^T may be overwritten by softmax(it+1)
+        // per K step; issued FIRST so that P^T is free again before phase A(it+1) wants to store into it
 #pragma unroll
         for (int kk = 0; kk < BT / 16; ++kk)
           umma_bf16_ts(tmem_base + TM_DV, tmem_base + TM_PT + kk * 8,
                        make_smem_desc_sw128(sDO(st) + kk * 2048, 16384, 1024), idesc_kv, (it | kk) != 0);
         umma_commit(pt_free);
+      }
+      __syncwarp();
+      if (it + 1 < n_it) issue_dp(it + 1);  // completes while phase A(it+1) runs
+      if (elect_one()) {
         // dK += dS^T Q
 #pragma unroll
         for (int kk = 0; kk < BT / 16; ++kk)
@@ -310,70 +343,98 @@ attn_bwd64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       if (threadIdx.x == 64) T64(0);
       float lse_next = 0.f;
       if (it + 1 < n_it) lse_next = fetch_lse(it + 1);  // latency hides behind this iteration's softmax
+      // ---------------- phase A: P^T = exp2(S^T * scale*log2e - lse*log2e), packed bf16 ----------------
       mbar_wait(s_full, it & 1u);
       tc_fence_after_sync();
       if (threadIdx.x == 64) T64(1);
-#pragma unroll 1
-      for (int c0 = cbase; c0 < cbase + 64; c0 += 32) {
-        uint32_t vs[32], vd[32];
+      uint32_t pk[32];  // this thread's 64 probabilities (key row x 64 query columns), kept for phase B
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        const int c0 = cbase + hf * 32;
+        uint32_t vs[32];
         tmem_ld_32x32b_x32(t_lane + TM_S + c0, vs);
-        tmem_ld_32x32b_x32(t_lane + TM_DP + c0, vd);
         tmem_ld_wait();
-        float ds[32];
-        uint32_t pk[16];
-        // dS here is P o (dP - delta) WITHOUT the softmax scale: dK and dQ are linear in dS, so the scale is
-        // applied once per output element (dK epilogue below, dQ conversion kernel) instead of once per score
         if (!need_mask) {
-          // packed fp32 pairs: exponent argument, dP - delta and the product cost one issue slot per TWO scores
+          // packed fp32 pairs: the exponent argument costs one issue slot per TWO scores
           const uint64_t sl2_2 = f2_pack(sl2, sl2);
 #pragma unroll
           for (int g = 0; g < 8; ++g) {
             const float4 l4 = *reinterpret_cast<const float4*>(lse2 + c0 + g * 4);
-            const float4 d4 = *reinterpret_cast<const float4*>(dlt + c0 + g * 4);
             float a0, a1, a2, a3;
             f2_unpack(f2_fma(f2_pack(__uint_as_float(vs[g * 4 + 0]), __uint_as_float(vs[g * 4 + 1])), sl2_2,
                              f2_pack(-l4.x, -l4.y)), a0, a1);
             f2_unpack(f2_fma(f2_pack(__uint_as_float(vs[g * 4 + 2]), __uint_as_float(vs[g * 4 + 3])), sl2_2,
                              f2_pack(-l4.z, -l4.w)), a2, a3);
-            const float e0 = ex2f(a0), e1 = ex2f(a1), e2 = ex2f(a2), e3 = ex2f(a3);
-            f2_unpack(f2_mul(f2_pack(e0, e1),
-                             f2_sub(f2_pack(__uint_as_float(vd[g * 4 + 0]), __uint_as_float(vd[g * 4 + 1])),
-                                    f2_pack(d4.x, d4.y))), ds[g * 4 + 0], ds[g * 4 + 1]);
-            f2_unpack(f2_mul(f2_pack(e2, e3),
-                             f2_sub(f2_pack(__uint_as_float(vd[g * 4 + 2]), __uint_as_float(vd[g * 4 + 3])),
-                                    f2_pack(d4.z, d4.w))), ds[g * 4 + 2], ds[g * 4 + 3]);
-            pk[g * 2] = pack_bf16x2(e0, e1);
-            pk[g * 2 + 1] = pack_bf16x2(e2, e3);
+            pk[hf * 16 + g * 2] = pack_bf16x2(ex2f(a0), ex2f(a1));
+            pk[hf * 16 + g * 2 + 1] = pack_bf16x2(ex2f(a2), ex2f(a3));
           }
         } else {
 #pragma unroll
           for (int g = 0; g < 8; ++g) {
             const float4 l4 = *reinterpret_cast<const float4*>(lse2 + c0 + g * 4);
-            const float4 d4 = *reinterpret_cast<const float4*>(dlt + c0 + g * 4);
             const float ls[4] = {l4.x, l4.y, l4.z, l4.w};
-            const float dl[4] = {d4.x, d4.y, d4.z, d4.w};
             float e[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const int qc = c0 + g * 4 + i;
               e[i] = ex2f(fmaf(__uint_as_float(vs[g * 4 + i]), sl2, -ls[i]));
               if ((diag && (q0 + qc < key)) || key >= p.S) e[i] = 0.f;
-              ds[g * 4 + i] = e[i] * (__uint_as_float(vd[g * 4 + i]) - dl[i]);
             }
-            pk[g * 2] = pack_bf16x2(e[0], e[1]);
-            pk[g * 2 + 1] = pack_bf16x2(e[2], e[3]);
+            pk[hf * 16 + g * 2] = pack_bf16x2(e[0], e[1]);
+            pk[hf * 16 + g * 2 + 1] = pack_bf16x2(e[2], e[3]);
           }
         }
         // P^T: queries c0 .. c0+31 of this key row = packed columns c0/2 .. c0/2+15.  The previous tile's
         // dV MMAs must have consumed the old contents first.
-        if (c0 == cbase && it > 0) {
+        if (hf == 0 && it > 0) {
           mbar_wait(pt_free, (it - 1) & 1u);
           tc_fence_after_sync();
         }
-        tmem_st_32x32b_x16(t_lane + TM_PT + (c0 >> 1), pk);
-#pragma unroll
-        for (int g = 0; g < 4; ++g) st_tile_chunk(sDS(bf), row, (c0 >> 3) + g, ds + g * 8);
+        tmem_st_32x32b_x16(t_lane + TM_PT + (c0 >> 1), pk + hf * 16);
       }
+      // lse*log2e of the NEXT iteration's queries goes to the other slot now, and only then is S^T handed back:
+      // S^T(it+1) completing (s_full) therefore implies every warp's lse(it+1) is in place, and -- because every
+      // warp arrives here after its last read of THIS iteration's lse -- the slot being overwritten (last read in
+      // phase A(it-1)) is no longer in use.  No CTA-wide barrier in the loop.
+      if (it + 1 < n_it && tid < 128) put_lse(it + 1, lse_next);
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_free);
+      if (threadIdx.x == 64) T64(4);
+      // ---------------- phase B: dS^T = P^T o (dP^T - delta)  (softmax scale folded out, see below) -------
+      // dS here is P o (dP - delta) WITHOUT the softmax scale: dK and dQ are linear in dS, so the scale is
+      // applied once per output element (dK epilogue below, dQ conversion kernel) instead of once per score.
+      // P is the bf16-rounded probability that also feeds dV (and that the forward kernel multiplied V with).
+      mbar_wait(dp_full, it & 1u);
+      tc_fence_after_sync();
+      if (threadIdx.x == 64) T64(6);
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        const int c0 = cbase + hf * 32;
+        uint32_t vd[32];
+        tmem_ld_32x32b_x32(t_lane + TM_DP + c0, vd);
+        tmem_ld_wait();
+        // (dP - delta) in packed fp32, rounded to bf16x2, times the bf16x2 probabilities in ONE bf16x2 multiply:
+        // the product is already the packed operand the dK / dQ MMAs read (3 issue slots per pair of scores)
+        uint32_t dsp[16];
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          const float4 d4 = *reinterpret_cast<const float4*>(dlt + c0 + g * 4);
+          float a0, a1, a2, a3;
+          f2_unpack(f2_sub(f2_pack(__uint_as_float(vd[g * 4 + 0]), __uint_as_float(vd[g * 4 + 1])), f2_pack(d4.x, d4.y)),
+                    a0, a1);
+          f2_unpack(f2_sub(f2_pack(__uint_as_float(vd[g * 4 + 2]), __uint_as_float(vd[g * 4 + 3])), f2_pack(d4.z, d4.w)),
+                    a2, a3);
+          dsp[g * 2] = mul_bf16x2(pk[hf * 16 + g * 2], pack_bf16x2(a0, a1));
+          dsp[g * 2 + 1] = mul_bf16x2(pk[hf * 16 + g * 2 + 1], pack_bf16x2(a2, a3));
+        }
+#pragma unroll
+        for (int g = 0; g < 4; ++g) st_tile_chunk_packed(sDS(bf), row, (c0 >> 3) + g, dsp + g * 4);
+      }
+      // delta of the next iteration's queries: parked BEFORE this warp reports phase B done, so dP^T(it+1)
+      // completing (dp_full, issued after all eight arrivals) implies the slot is complete; its previous contents
+      // (iteration it-1) were last read before pds_full(it-1), which dp_full(it) -- already observed -- followed
+      if (it + 1 < n_it && tid >= 128) put_lse(it + 1, lse_next);
       tmem_st_wait();
       tc_fence_before_sync();
       fence_proxy_async_smem();
@@ -381,10 +442,6 @@ attn_bwd64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       if (lane == 0) mbar_arrive(pds_full);
       if (threadIdx.x == 64) T64(2);
 
-      if (it + 1 < n_it) put_lse(it + 1, lse_next);  // visible after the barriers below, before softmax(it+1)
-      if (threadIdx.x == 64) T64(3);
-      named_bar_sync(1, 256);  // lse/delta slot of it+1 complete before anyone reads it
-      if (threadIdx.x == 64) T64(5);
     }
     // the softmax warps do not follow dq_full's phases, so a parity wait on it could alias: dedicated barrier
     mbar_wait(all_done, 0);

@@ -173,66 +173,9 @@ rmsnorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ dres, const T
 // ---- CTA, so the loads of one row overlap the reduction and stores of its neighbours ------------------
 constexpr int RW_WARPS = RN_THREADS / 32;
 
-template <typename T, int NVW>
-__global__ void __launch_bounds__(RN_THREADS)
-rmsnorm_fwd_warp_kernel(const T* __restrict__ x, const T* __restrict__ delta, const T* __restrict__ w,
-                        T* __restrict__ sum_out, T* __restrict__ y, float* __restrict__ rstd_out, int rows,
-                        int H, float eps) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float wv[NVW][8];
-#pragma unroll
-  for (int v = 0; v < NVW; ++v) {
-    const int col = (v * 32 + lane) * 8;
-    if (col < H) ld8(w + col, wv[v]);
-  }
-  for (int row = blockIdx.x * RW_WARPS + warp; row < rows; row += gridDim.x * RW_WARPS) {
-    const long long base = (long long)row * H;
-    float xv[NVW][8];
-#pragma unroll
-    for (int v = 0; v < NVW; ++v) {
-      const int col = (v * 32 + lane) * 8;
-      if (col < H) ld8(x + base + col, xv[v]);
-    }
-    if (delta) {
-#pragma unroll
-      for (int v = 0; v < NVW; ++v) {
-        const int col = (v * 32 + lane) * 8;
-        if (col < H) {
-          float dv[8];
-          ld8(delta + base + col, dv);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) xv[v][j] = round_like(xv[v][j] + dv[j], x);
-          st8(sum_out + base + col, xv[v]);
-        }
-      }
-    }
-    float ss = 0.f;
-#pragma unroll
-    for (int v = 0; v < NVW; ++v) {
-      const int col = (v * 32 + lane) * 8;
-      if (col < H) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) ss += xv[v][j] * xv[v][j];
-      }
-    }
-    const float tot = warp_sum(ss);
-    const float rstd = 1.0f / sqrtf(tot / (float)H + eps);
-    if (lane == 0 && rstd_out) rstd_out[row] = rstd;
-#pragma unroll
-    for (int v = 0; v < NVW; ++v) {
-      const int col = (v * 32 + lane) * 8;
-      if (col < H) {
-        float o[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = xv[v][j] * rstd * wv[v][j];
-        st8(y + base + col, o);
-      }
-    }
-  }
-}
-
-// Packed row segments: the backward pass keeps x and dy of the whole row in registers between the two
-// passes (dot product, then dx); holding bf16 rows packed halves that footprint and buys a fourth CTA per SM.
+// Row segments are held PACKED (bf16 rows as uint4) between the two passes and the gain vector is re-read from
+// L1 (2 KB) instead of living in registers: ~56 registers, so 8 CTAs (32 warps) per SM keep enough 16-byte loads
+// in flight to cover HBM latency (the first version: 94 registers, 4 CTAs, 0.46 of the HBM roofline under ncu).
 template <typename T> struct Raw8;
 template <> struct Raw8<__nv_bfloat16> { uint4 r; };
 template <> struct Raw8<float> { float4 a, b; };
@@ -253,9 +196,82 @@ __device__ __forceinline__ void unraw(const Raw8<float>& i, float* f) {
   f[0] = i.a.x; f[1] = i.a.y; f[2] = i.a.z; f[3] = i.a.w;
   f[4] = i.b.x; f[5] = i.b.y; f[6] = i.b.z; f[7] = i.b.w;
 }
+__device__ __forceinline__ void toraw(const float* f, Raw8<__nv_bfloat16>& o) {
+  o.r.x = pack_bf16x2(f[0], f[1]);
+  o.r.y = pack_bf16x2(f[2], f[3]);
+  o.r.z = pack_bf16x2(f[4], f[5]);
+  o.r.w = pack_bf16x2(f[6], f[7]);
+}
+__device__ __forceinline__ void toraw(const float* f, Raw8<float>& o) {
+  o.a = make_float4(f[0], f[1], f[2], f[3]);
+  o.b = make_float4(f[4], f[5], f[6], f[7]);
+}
+__device__ __forceinline__ void straw(__nv_bfloat16* p, const Raw8<__nv_bfloat16>& i) {
+  *reinterpret_cast<uint4*>(p) = i.r;
+}
+__device__ __forceinline__ void straw(float* p, const Raw8<float>& i) {
+  *reinterpret_cast<float4*>(p) = i.a;
+  *reinterpret_cast<float4*>(p + 4) = i.b;
+}
 
 template <typename T, int NVW>
-__global__ void __launch_bounds__(RN_THREADS, 4)
+__global__ void __launch_bounds__(RN_THREADS, (sizeof(T) == 2) ? 8 : 4)
+rmsnorm_fwd_warp_kernel(const T* __restrict__ x, const T* __restrict__ delta, const T* __restrict__ w,
+                        T* __restrict__ sum_out, T* __restrict__ y, float* __restrict__ rstd_out, int rows,
+                        int H, float eps) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int row = blockIdx.x * RW_WARPS + warp; row < rows; row += gridDim.x * RW_WARPS) {
+    const long long base = (long long)row * H;
+    Raw8<T> xr[NVW], dr[NVW];
+#pragma unroll
+    for (int v = 0; v < NVW; ++v) {
+      const int col = (v * 32 + lane) * 8;
+      if (col < H) {
+        ldraw(x + base + col, xr[v]);
+        if (delta) ldraw(delta + base + col, dr[v]);
+      }
+    }
+    float ss = 0.f;
+#pragma unroll
+    for (int v = 0; v < NVW; ++v) {
+      const int col = (v * 32 + lane) * 8;
+      if (col < H) {
+        float xv[8];
+        unraw(xr[v], xv);
+        if (delta) {
+          float dv[8];
+          unraw(dr[v], dv);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) xv[j] = round_like(xv[j] + dv[j], x);
+          toraw(xv, xr[v]);  // exact: the sum was just rounded to the storage type
+          straw(sum_out + base + col, xr[v]);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ss += xv[j] * xv[j];
+      }
+    }
+    const float tot = warp_sum(ss);
+    const float rstd = 1.0f / sqrtf(tot / (float)H + eps);
+    if (lane == 0 && rstd_out) rstd_out[row] = rstd;
+#pragma unroll
+    for (int v = 0; v < NVW; ++v) {
+      const int col = (v * 32 + lane) * 8;
+      if (col < H) {
+        float xv[8], wv[8], o[8];
+        unraw(xr[v], xv);
+        ld8(w + col, wv);  // 2 KB gain vector: L1-resident
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = xv[j] * rstd * wv[j];
+        st8(y + base + col, o);
+      }
+    }
+  }
+}
+
+// Backward: x, dy (and the residual-stream gradient, when fused) of the whole row stay packed in registers between
+// the two passes; all three are requested up front so that one HBM latency covers them.
+template <typename T, int NVW>
+__global__ void __launch_bounds__(RN_THREADS, (sizeof(T) == 2) ? 5 : 3)
 rmsnorm_bwd_warp_kernel(const T* __restrict__ dy, const T* __restrict__ dres, const T* __restrict__ x,
                         const T* __restrict__ w, const float* __restrict__ rstd_in, T* __restrict__ dx,
                         float* __restrict__ dw_part, int rows, int H) {
@@ -270,13 +286,14 @@ rmsnorm_bwd_warp_kernel(const T* __restrict__ dy, const T* __restrict__ dres, co
   for (int row = blockIdx.x * RW_WARPS + warp; row < rows; row += gridDim.x * RW_WARPS) {
     const long long base = (long long)row * H;
     const float rstd = rstd_in[row];
-    Raw8<T> xr[NVW], gr[NVW];
+    Raw8<T> xr[NVW], gr[NVW], rr[NVW];
 #pragma unroll
     for (int v = 0; v < NVW; ++v) {
       const int col = (v * 32 + lane) * 8;
       if (col < H) {
         ldraw(x + base + col, xr[v]);
         ldraw(dy + base + col, gr[v]);
+        if (dres) ldraw(dres + base + col, rr[v]);  // requested with x and dy: no second, serialised HBM latency
       }
     }
     float dot = 0.f;
@@ -309,7 +326,7 @@ rmsnorm_bwd_warp_kernel(const T* __restrict__ dy, const T* __restrict__ dres, co
         for (int j = 0; j < 8; ++j) o[j] = rstd * (gv[j] * wv[j] - xv[j] * c);
         if (dres) {
           float r[8];
-          ld8(dres + base + col, r);
+          unraw(rr[v], r);
 #pragma unroll
           for (int j = 0; j < 8; ++j) o[j] += r[j];
         }
@@ -442,7 +459,7 @@ int rmsnorm_fwd_t(const T* x, const T* delta, const T* w, T* sum_out, T* y, floa
 inline int rmsnorm_bwd_grid(int rows, int H) {
   if (H <= RW_MAX_H) {
     const int want = (rows + RW_WARPS - 1) / RW_WARPS;
-    return want < num_sms() * 4 ? want : num_sms() * 4;
+    return want < num_sms() * 5 ? want : num_sms() * 5;
   }
   return rows < num_sms() * 4 ? rows : num_sms() * 4;
 }

@@ -16,8 +16,8 @@ os.environ["B200_ATTN_TRACE"] = hex(trace.data_ptr())
 ops.attention_bwd_raw(q, k, v, o, do, lse, D ** -0.5, True)
 torch.cuda.synchronize()
 t = trace.cpu().view(16, 16)
-names = {0: "sm.top", 1: "sm.s_full", 2: "sm.pds_arrive", 3: "sm.lse_put", 5: "sm.bar",
-         8: "mma.top", 9: "mma.pds_full", 10: "mma.S(it+1) issued", 11: "mma.dq_empty", 12: "mma.dVdKdQ issued",
+names = {0: "sm.top", 1: "sm.s_full", 4: "sm.phaseA_done", 6: "sm.dp_full", 2: "sm.pds_arrive", 3: "sm.lse_put", 5: "sm.bar",
+         8: "mma.top", 9: "mma.S(it+1) issued", 10: "mma.pds_full", 11: "mma.dq_empty", 12: "mma.dVdKdQ issued",
          13: "drain.dq_full", 14: "drain.reds issued"}
 base = int(t[0, 8])
 for it in range(6):
