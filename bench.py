@@ -424,8 +424,22 @@ def run_workload(tag: str, K: int, W: int, with_e2e: bool = True, with_dp_check:
             # ONE update from identical state through every exchange implementation: the fused GEMM -> all-gather
             # peer stores (unicast, NVSwitch multicast) must reproduce the plain NCCL all-gather's parameters
             store = tr.store
-            snap = (store.master.clone(), opt._buf.clone(), opt.count)
-            fixed = [tr.data_manager.generate_batch(10 ** 6 + j).to(dev) for j in range(k)]
+            # gradients of one fixed batch, computed and all-reduced ONCE (the backward's fp32 dQ atomics are not
+            # bit-reproducible, and Newton-Schulz amplifies such noise): every mode starts from the same bits
+            store.zero_grad()
+            tr._accum_step = 0
+            for j in range(k):
+                fb = tr.data_manager.generate_batch(10 ** 6 + j).to(dev)
+                l_, _ = tr.compute_loss(tr.model, fb[:, :-1], fb[:, 1:])
+                l_.backward()
+                if tr.use_acc:
+                    ops.clip_accum(store.grad, store.acc, tr.clip_value, 1.0 / k, init=(j == 0))
+                    store.zero_grad()
+            gsrc = store.acc if tr.use_acc else store.grad
+            dp.all_reduce_sum_(gsrc)
+            snap = (store.master.clone(), opt._buf.clone(), opt.count, gsrc.clone())
+            alt = getattr(opt, "alternate_optimizer", None)
+            alt_snap = (alt._m.clone(), alt._v.clone(), alt.count) if alt is not None and hasattr(alt, "_m") else None
             results = {}
             for mode in ("nccl", "unicast", "multicast"):
                 eff = opt.set_exchange(mode)
@@ -433,10 +447,10 @@ def run_workload(tag: str, K: int, W: int, with_e2e: bool = True, with_dp_check:
                     results[mode] = {"available": False, "effective": eff}
                     continue
                 store.master.copy_(snap[0]); store.refresh_shadow(); opt._buf.copy_(snap[1]); opt.count = snap[2]
-                store.zero_grad()
-                tr._accum_step = 0
-                for j in range(k):
-                    tr.micro_step(10 ** 6 + j, fixed[j])
+                gsrc.copy_(snap[3])
+                if alt_snap is not None:
+                    alt._m.copy_(alt_snap[0]); alt._v.copy_(alt_snap[1]); alt.count = alt_snap[2]
+                tr.optimizer.update(tr.model)
                 torch.cuda.synchronize()
                 upd = store.master - snap[0]
                 fpm = master_fingerprint(store)
@@ -449,8 +463,8 @@ def run_workload(tag: str, K: int, W: int, with_e2e: bool = True, with_dp_check:
             for mode, r in results.items():
                 u = r.pop("_upd", None)
                 if u is not None and ref is not None and mode != "nccl":
-                    # ownership differs between the modes (flop-balanced vs equal chunks), which changes the split-K
-                    # choice of a few GEMMs: equal up to fp32 summation order inside bf16 outputs
+                    # same gradients, same momentum: ownership (flop-balanced vs equal chunks) only changes which rank
+                    # computes a matrix and, through the batch size of a launch, the split-K choice of a few GEMMs
                     r["max_rel_update_diff_vs_nccl"] = float((u - ref).norm() / (ref.norm() + 1e-30))
                     r["bit_identical_to_nccl"] = bool(torch.equal(u, ref))
             opt.set_exchange("auto")
