@@ -200,6 +200,20 @@ int b200_add_rmsnorm_bwd(const void* dy, const void* dres, const void* x, const 
 int b200_rope(const void* x, void* y, const float* cos_t, const float* sin_t, int B, int S, int NH,
               int D, int backward, int is_bf16, void* stream);
 
+/* ---- MLP block on the in-tree GEMM engine with the GLU in the epilogue ----------------
+ * arch/llama.py:142-151: down( gate(x) * sigmoid(up(x)) * 2 ).  gate_proj.weight and up_proj.weight must be
+ * adjacent in memory (W2 = [Wg ; Wu], [2I, K] row-major; flat.ParamStore lays them out that way).
+ * b200_mlp_gateup_glu_fwd:  gu[M, 2I] = x[M, K] W2^T  (columns [0, I) = gate(x), [I, 2I) = up(x)),
+ *                           y[M, I] = gate * sigmoid(up) * 2 from the fp32 accumulators -- one tcgen05 kernel,
+ *                           no separate activation pass.  K % 8 == 0, I % 128 == 0.
+ * b200_mlp_down_glu_bwd:    d = dy[M, H] Wd (dgrad of down_proj, Wd = down_proj.weight [H, I]) never leaves the
+ *                           chip: dgu[M, 2I] = [ d * sigmoid(u) * 2 | d * g * sigmoid(u) * (1 - sigmoid(u)) * 2 ]
+ *                           with g, u read from the saved gu.  [dg | du] is one matrix, so the gate/up dgrad and
+ *                           wgrad each run as a single GEMM against W2. */
+int b200_mlp_gateup_glu_fwd(const void* x, const void* W2, void* gu, void* y, int M, int K, int I, void* stream);
+int b200_mlp_down_glu_bwd(const void* dy, const void* Wd, const void* gu, void* dgu, int M, int H, int I,
+                          void* stream);
+
 /* ---- block-adjacent fused elementwise steps ------------------------------------
  * arch/llama.py:151: y = gate * sigmoid(up) * 2 and its adjoint; bf16, n % 8 == 0 */
 int b200_glu_fwd(const void* gate, const void* up, void* y, long long n, void* stream);

@@ -52,6 +52,8 @@ SIGNATURES = {
     "b200_add_rmsnorm_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _i, _vp]),
     "b200_add_rmsnorm_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _sz, _vp]),
     "b200_rope": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "b200_mlp_gateup_glu_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "b200_mlp_down_glu_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "b200_glu_fwd": (_i, [_vp, _vp, _vp, _ll, _vp]),
     "b200_glu_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _ll, _vp]),
     "b200_ce_fwd": (_i, [_vp, _ll, _vp, _i, _i, _ll, _vp, _vp, _vp]),

@@ -73,8 +73,7 @@ class MLP(nn.Module):
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         if self.gate_proj.bias is not None:
             return self.down_proj(ops.glu(self.gate_proj(x), self.up_proj(x)))
-        g, u = ops.multi_linear(x, (self.gate_proj.weight, self.up_proj.weight))
-        return ops.linear(ops.glu(g, u), self.down_proj.weight)
+        return ops.mlp(x, self.gate_proj.weight, self.up_proj.weight, self.down_proj.weight)
 
 
 class AttentionModule(nn.Module):

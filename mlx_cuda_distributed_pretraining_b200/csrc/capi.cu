@@ -25,6 +25,9 @@ struct NsGroup {
 size_t newton_schulz_multi_workspace_bytes(const NsGroup* g, int n, int steps);
 int newton_schulz_multi(const NsGroup* g, int n, int steps, float a, float b, float c, void* ws, size_t ws_bytes,
                         cudaStream_t stream);
+int gemm_glu_fwd_2cta(const void* x, const void* W2, void* gu, void* y, int M, int K, int I, cudaStream_t stream);
+int gemm_glu_bwd_2cta(const void* dy, const void* Wd, const void* gu, void* dgu, int M, int H, int I,
+                      cudaStream_t stream);
 size_t reduce_workspace_bytes(int batch);
 int muon_momentum(const void* g, int g_is_bf16, float* buf, void* u_bf16, float* sumsq,
                   long long numel, int batch, float mu, int nesterov, float gscale, void* ws,
@@ -140,6 +143,13 @@ int b200_newton_schulz_multi(const b200_ns_group* groups, int n_groups, int step
                              void* workspace, size_t workspace_bytes, void* stream) {
   return b200::newton_schulz_multi(reinterpret_cast<const b200::NsGroup*>(groups), n_groups, steps, a, b, c, workspace,
                                    workspace_bytes, S_(stream));
+}
+int b200_mlp_gateup_glu_fwd(const void* x, const void* W2, void* gu, void* y, int M, int K, int I, void* stream) {
+  return b200::gemm_glu_fwd_2cta(x, W2, gu, y, M, K, I, S_(stream));
+}
+int b200_mlp_down_glu_bwd(const void* dy, const void* Wd, const void* gu, void* dgu, int M, int H, int I,
+                          void* stream) {
+  return b200::gemm_glu_bwd_2cta(dy, Wd, gu, dgu, M, H, I, S_(stream));
 }
 size_t b200_reduce_workspace_bytes(int batch) { return b200::reduce_workspace_bytes(batch); }
 int b200_muon_momentum(const void* g, int g_is_bf16, float* buf, void* u_bf16, float* sumsq,

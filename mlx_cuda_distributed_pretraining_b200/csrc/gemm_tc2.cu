@@ -44,6 +44,15 @@ struct Gemm2Args {
   int n_peers;
   void* peer_D[7];
   int staged_epi;  // use the coalescing (smem-transposed) epilogue even without peers
+  // fused MLP epilogues (EPI template parameter; arch/llama.py:149-151 of the reference):
+  //   EPI 1  [g | u] = x [Wg ; Wu]^T with y = g * sigmoid(u) * 2 computed from the fp32 accumulators: pair tile =
+  //          128 gate columns (leader CTA's B rows) + the SAME 128 up columns (peer CTA's B rows at +glu_I);
+  //          D = gu [M, 2*glu_I] (ldd = 2*glu_I), aux = y [M, glu_I]
+  //   EPI 2  d = dy Wd (dgrad of down_proj) with the GLU adjoint applied to the accumulator: aux = gu (read),
+  //          D = [dg | du] [M, 2*glu_I], dg = d*sigmoid(u)*2, du = d*g*sigmoid(u)*(1-sigmoid(u))*2
+  int glu_I;
+  void* aux;
+  long long ld_aux;
 };
 constexpr int G2_MAX_PEERS = 7;
 
@@ -353,7 +362,166 @@ __device__ __forceinline__ void g2_epilogue_tile(const G2Tile& t, uint32_t tmem_
   if (lane == 0) mbar_arrive_cluster(tempty, 0);
 }
 
-template <bool A_MN, bool B_MN, typename OutT, int BN>
+
+// sigmoid on the special-function unit: ex2.approx + rcp.approx (two MUFU ops, no IEEE division sequence)
+__device__ __forceinline__ float g2_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+
+// Per-warp staging tile [32 rows x 64 B] (16-byte pieces XOR-swizzled by row pair, conflict-free both ways): lanes own
+// ROWS when they produce / consume values (TMEM lane = row) but a global access instruction should cover few rows and
+// whole 64-byte runs -- 8 rows x 64 B per instruction instead of 32 rows x 16 B (4x fewer LSU wavefronts / L2 requests).
+__device__ __forceinline__ void g2_stage_put_row(uint32_t stg, int lane, const uint32_t* w16) {
+#pragma unroll
+  for (int piece = 0; piece < 4; ++piece)
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + lane * 64 + ((piece ^ ((lane >> 1) & 3)) << 4)),
+                 "r"(w16[piece * 4 + 0]), "r"(w16[piece * 4 + 1]), "r"(w16[piece * 4 + 2]), "r"(w16[piece * 4 + 3])
+                 : "memory");
+}
+__device__ __forceinline__ void g2_stage_get_row(uint32_t stg, int lane, uint32_t* w16) {
+#pragma unroll
+  for (int piece = 0; piece < 4; ++piece)
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(w16[piece * 4 + 0]), "=r"(w16[piece * 4 + 1]), "=r"(w16[piece * 4 + 2]), "=r"(w16[piece * 4 + 3])
+                 : "r"(stg + lane * 64 + ((piece ^ ((lane >> 1) & 3)) << 4)));
+}
+// staged tile -> global: rows row0 .. row0+31 of a row-major bf16 matrix, 32 columns starting at col0
+__device__ __forceinline__ void g2_stage_store(uint32_t stg, int lane, __nv_bfloat16* base, long long ld, int row0,
+                                               int col0, int M, int ncols) {
+  const int piece = lane & 3;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = i * 8 + (lane >> 2);
+    uint4 o;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(o.x), "=r"(o.y), "=r"(o.z), "=r"(o.w)
+                 : "r"(stg + r * 64 + ((piece ^ ((r >> 1) & 3)) << 4)));
+    if (row0 + r < M && col0 + piece * 8 < ncols) stg128(base + (long long)(row0 + r) * ld + col0 + piece * 8, o);
+  }
+}
+// global -> registers in the coalesced pattern (4 x 16 B per lane); g2_stage_fill parks them in the staging tile
+__device__ __forceinline__ void g2_coalesced_load(const __nv_bfloat16* base, long long ld, int row0, int col0, int M,
+                                                  int ncols, int lane, uint4* o4) {
+  const int piece = lane & 3;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = i * 8 + (lane >> 2);
+    o4[i] = (row0 + r < M && col0 + piece * 8 < ncols) ? ldg128(base + (long long)(row0 + r) * ld + col0 + piece * 8)
+                                                       : make_uint4(0, 0, 0, 0);
+  }
+}
+__device__ __forceinline__ void g2_stage_fill(uint32_t stg, int lane, const uint4* o4) {
+  const int piece = lane & 3;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = i * 8 + (lane >> 2);
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + r * 64 + ((piece ^ ((r >> 1) & 3)) << 4)),
+                 "r"(o4[i].x), "r"(o4[i].y), "r"(o4[i].z), "r"(o4[i].w)
+                 : "memory");
+  }
+}
+
+// EPI 1: one epilogue warp = 32 rows x 64 gate columns + the matching 64 up columns of a [256 x (128 | 128)] pair tile
+__device__ __forceinline__ void g2_epilogue_glu_fwd(const Gemm2Args& p, int b, int mi, int ni, uint32_t tmem_base,
+                                                    uint32_t acc, uint32_t acc_phase, uint32_t tfull, uint32_t tempty,
+                                                    uint32_t epi_stage, int warp, int lane, uint32_t rank) {
+  constexpr int BN = 256;
+  const int q = warp & 3;
+  const int hsel = (warp - 4) >> 2;  // which 64-column half of the 128 gate / up columns
+  const int row0 = mi * 256 + (int)rank * 128 + q * 32;
+  const int col0 = ni * 128 + hsel * 64;  // feature index of this warp's first column
+  __nv_bfloat16* gu = reinterpret_cast<__nv_bfloat16*>(p.D) + (long long)b * p.strideD;
+  __nv_bfloat16* yb = reinterpret_cast<__nv_bfloat16*>(p.aux);
+  const uint32_t stg = epi_stage + (uint32_t)(warp - 4) * 4096u;  // two 2 KB tiles per warp
+  mbar_wait(tfull, acc_phase);
+  tc_fence_after_sync();
+  const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + acc * BN;
+#pragma unroll
+  for (int cc = 0; cc < 64; cc += 32) {
+    uint32_t vg[32], vu[32];
+    tmem_ld_32x32b_x32(t_row + hsel * 64 + cc, vg);
+    tmem_ld_32x32b_x32(t_row + 128 + hsel * 64 + cc, vu);
+    tmem_ld_wait();
+    uint32_t wg[16], wu[16], wy[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float g0 = __uint_as_float(vg[2 * i]), g1 = __uint_as_float(vg[2 * i + 1]);
+      const float u0 = __uint_as_float(vu[2 * i]), u1 = __uint_as_float(vu[2 * i + 1]);
+      wg[i] = pack_bf16x2(g0, g1);
+      wu[i] = pack_bf16x2(u0, u1);
+      wy[i] = pack_bf16x2(g0 * g2_sigmoid(u0) * 2.0f, g1 * g2_sigmoid(u1) * 2.0f);
+    }
+    g2_stage_put_row(stg, lane, wg);
+    g2_stage_put_row(stg + 2048, lane, wu);
+    __syncwarp();
+    g2_stage_store(stg, lane, gu, p.ldd, row0, col0 + cc, p.M, p.glu_I);
+    g2_stage_store(stg + 2048, lane, gu + p.glu_I, p.ldd, row0, col0 + cc, p.M, p.glu_I);
+    __syncwarp();
+    g2_stage_put_row(stg, lane, wy);
+    __syncwarp();
+    g2_stage_store(stg, lane, yb, p.ld_aux, row0, col0 + cc, p.M, p.glu_I);
+    __syncwarp();
+  }
+  tc_fence_before_sync();
+  __syncwarp();
+  if (lane == 0) mbar_arrive_cluster(tempty, 0);
+}
+
+// EPI 2: standard [256 x 256] pair tile of d = dy Wd; one epilogue warp = 32 rows x 128 columns
+__device__ __forceinline__ void g2_epilogue_glu_bwd(const Gemm2Args& p, int b, int mi, int ni, uint32_t tmem_base,
+                                                    uint32_t acc, uint32_t acc_phase, uint32_t tfull, uint32_t tempty,
+                                                    uint32_t epi_stage, int warp, int lane, uint32_t rank) {
+  constexpr int BN = 256;
+  const int q = warp & 3;
+  const int cbase = ((warp - 4) >> 2) * 128;
+  const int row0 = mi * 256 + (int)rank * 128 + q * 32;
+  const int n0 = ni * BN + cbase;
+  const __nv_bfloat16* gu = reinterpret_cast<const __nv_bfloat16*>(p.aux);
+  __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.D) + (long long)b * p.strideD;
+  const uint32_t stg = epi_stage + (uint32_t)(warp - 4) * 4096u;
+  // the first chunk's g / u are requested (coalesced: 8 rows x 64 B per instruction) before the accumulator is ready
+  uint4 pg[4], pu[4];
+  g2_coalesced_load(gu, p.ld_aux, row0, n0, p.M, p.glu_I, lane, pg);
+  g2_coalesced_load(gu + p.glu_I, p.ld_aux, row0, n0, p.M, p.glu_I, lane, pu);
+  mbar_wait(tfull, acc_phase);
+  tc_fence_after_sync();
+  const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + acc * BN;
+#pragma unroll 1
+  for (int cc = 0; cc < 128; cc += 32) {
+    uint32_t v[32];
+    tmem_ld_32x32b_x32(t_row + cbase + cc, v);
+    g2_stage_fill(stg, lane, pg);
+    g2_stage_fill(stg + 2048, lane, pu);
+    if (cc + 32 < 128) {  // next chunk's g / u in flight while this one is processed
+      g2_coalesced_load(gu, p.ld_aux, row0, n0 + cc + 32, p.M, p.glu_I, lane, pg);
+      g2_coalesced_load(gu + p.glu_I, p.ld_aux, row0, n0 + cc + 32, p.M, p.glu_I, lane, pu);
+    }
+    __syncwarp();
+    uint32_t gw[16], uw[16];
+    g2_stage_get_row(stg, lane, gw);
+    g2_stage_get_row(stg + 2048, lane, uw);
+    tmem_ld_wait();
+    uint32_t w1[16], w2[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float2 gg = unpack_bf16x2(gw[i]), uu = unpack_bf16x2(uw[i]);
+      const float d0 = __uint_as_float(v[2 * i]), d1 = __uint_as_float(v[2 * i + 1]);
+      const float s0 = g2_sigmoid(uu.x), s1 = g2_sigmoid(uu.y);
+      w1[i] = pack_bf16x2(d0 * s0 * 2.0f, d1 * s1 * 2.0f);
+      w2[i] = pack_bf16x2(d0 * gg.x * s0 * (1.0f - s0) * 2.0f, d1 * gg.y * s1 * (1.0f - s1) * 2.0f);
+    }
+    __syncwarp();
+    g2_stage_put_row(stg, lane, w1);
+    g2_stage_put_row(stg + 2048, lane, w2);
+    __syncwarp();
+    g2_stage_store(stg, lane, out, p.ldd, row0, n0 + cc, p.M, p.glu_I);
+    g2_stage_store(stg + 2048, lane, out + p.glu_I, p.ldd, row0, n0 + cc, p.M, p.glu_I);
+    __syncwarp();
+  }
+  tc_fence_before_sync();
+  __syncwarp();
+  if (lane == 0) mbar_arrive_cluster(tempty, 0);
+}
+
+template <bool A_MN, bool B_MN, typename OutT, int BN, int EPI = 0>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
 gemm2_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const Gemm2Args p) {
@@ -429,7 +597,8 @@ gemm2_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         int mi, ni;
         tile_coords(p.symmetric, p.tiles_n, tile - b * tiles_per_batch, mi, ni);
         const int m0 = mi * 256 + (int)rank * 128;
-        const int n0 = ni * BN + (int)rank * BNH;
+        // EPI 1: the leader loads 128 rows of Wg, the peer the SAME 128 rows of Wu (stacked glu_I rows further down)
+        const int n0 = (EPI == 1) ? ni * 128 + (int)rank * p.glu_I : ni * BN + (int)rank * BNH;
         for (int kb = kb_begin; kb < kb_end; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const int k0 = kb * G2_BK;
@@ -507,6 +676,17 @@ gemm2_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     for (int w = cluster_id; w < total_work; w += num_clusters, ++iter) {
       const int tile = w / p.k_splits;
       const int b = tile / tiles_per_batch;
+      if constexpr (EPI != 0) {
+        int mi, ni;
+        tile_coords(0, p.tiles_n, tile - b * tiles_per_batch, mi, ni);
+        if constexpr (EPI == 1)
+          g2_epilogue_glu_fwd(p, b, mi, ni, tmem_base, iter & 1u, (iter >> 1) & 1u, tfull_bar(iter & 1u),
+                              tempty_bar(iter & 1u), epi_stage, warp, lane, rank);
+        else
+          g2_epilogue_glu_bwd(p, b, mi, ni, tmem_base, iter & 1u, (iter >> 1) & 1u, tfull_bar(iter & 1u),
+                              tempty_bar(iter & 1u), epi_stage, warp, lane, rank);
+        continue;
+      }
       G2Tile t;
       t.M = p.M;
       t.N = p.N;
@@ -823,10 +1003,10 @@ gemm2_grouped_kernel(const __grid_constant__ G2GArgs g) {
   }
 }
 
-template <bool A_MN, bool B_MN, typename OutT, int BN>
+template <bool A_MN, bool B_MN, typename OutT, int BN, int EPI = 0>
 int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gemm2Args& args, cudaStream_t stream) {
   using Cfg = G2Cfg<BN>;
-  auto kern = gemm2_bf16_tc_kernel<A_MN, B_MN, OutT, BN>;
+  auto kern = gemm2_bf16_tc_kernel<A_MN, B_MN, OutT, BN, EPI>;
   static bool attr_set = false;
   if (!attr_set) {
     B200_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -867,6 +1047,77 @@ int dispatch2(bool out_f32, int bn, const CUtensorMap& tmA, const CUtensorMap& t
 
 }  // namespace
 
+
+// ---- fused MLP GEMMs (arch/llama.py:142-151: down(gate(x) * sigmoid(up(x)) * 2)) --------------------------
+static int glu_common_args(Gemm2Args& a, int M, int N_tiles_n, int K, int I, void* D, long long ldd, void* aux,
+                           long long ld_aux) {
+  a = Gemm2Args{};
+  a.M = M;
+  a.N = I;
+  a.K = K;
+  a.batch = 1;
+  a.tiles_m = (M + 255) / 256;
+  a.tiles_n = N_tiles_n;
+  a.alpha = 1.0f;
+  a.beta = 0.0f;
+  a.D = D;
+  a.ldd = ldd;
+  a.strideD = 0;
+  a.k_splits = 1;
+  a.glu_I = I;
+  a.aux = aux;
+  a.ld_aux = ld_aux;
+  return 0;
+}
+
+// gu[M, 2I] = x[M, K] [Wg ; Wu]^T (W2: [2I, K] row-major, gate rows first), y[M, I] = g * sigmoid(u) * 2
+int gemm_glu_fwd_2cta(const void* x, const void* W2, void* gu, void* y, int M, int K, int I, cudaStream_t stream) {
+  B200_CHECK_ARG(M > 0 && K > 0 && I > 0 && K % 8 == 0 && I % 128 == 0,
+                 "mlp_glu_fwd: need K %% 8 == 0 and intermediate size %% 128 == 0 (M=%d K=%d I=%d)", M, K, I);
+  CUtensorMap tmA, tmB;
+  {
+    const uint64_t dims[3] = {(uint64_t)K, (uint64_t)M, 1};
+    const uint64_t strides[2] = {(uint64_t)K * 2, (uint64_t)M * K * 2};
+    const uint32_t box[3] = {64, 128, 1};
+    int rc = make_tensor_map(&tmA, x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 3, dims, strides, box, true);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t dims[3] = {(uint64_t)K, (uint64_t)(2 * I), 1};
+    const uint64_t strides[2] = {(uint64_t)K * 2, (uint64_t)2 * I * K * 2};
+    const uint32_t box[3] = {64, 128, 1};
+    int rc = make_tensor_map(&tmB, W2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 3, dims, strides, box, true);
+    if (rc) return rc;
+  }
+  Gemm2Args a;
+  glu_common_args(a, M, I / 128, K, I, gu, 2LL * I, y, I);
+  return launch_gemm2<false, false, __nv_bfloat16, 256, 1>(tmA, tmB, a, stream);
+}
+
+// dgu[M, 2I] = GLU adjoint of d = dy[M, H] Wd (Wd: [H, I] row-major = down_proj.weight), gu[M, 2I] the saved
+// forward activations: dg = d * sigmoid(u) * 2 ; du = d * g * sigmoid(u) * (1 - sigmoid(u)) * 2
+int gemm_glu_bwd_2cta(const void* dy, const void* Wd, const void* gu, void* dgu, int M, int H, int I,
+                      cudaStream_t stream) {
+  B200_CHECK_ARG(M > 0 && H > 0 && I > 0 && H % 8 == 0 && I % 8 == 0, "mlp_glu_bwd: bad shape M=%d H=%d I=%d", M, H, I);
+  CUtensorMap tmA, tmB;
+  {
+    const uint64_t dims[3] = {(uint64_t)H, (uint64_t)M, 1};
+    const uint64_t strides[2] = {(uint64_t)H * 2, (uint64_t)M * H * 2};
+    const uint32_t box[3] = {64, 128, 1};
+    int rc = make_tensor_map(&tmA, dy, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 3, dims, strides, box, true);
+    if (rc) return rc;
+  }
+  {  // B[n = i, k = h] = Wd[h, i]: stored [K = H rows][N = I]: MN-major
+    const uint64_t dims[3] = {(uint64_t)I, (uint64_t)H, 1};
+    const uint64_t strides[2] = {(uint64_t)I * 2, (uint64_t)H * I * 2};
+    const uint32_t box[3] = {64, (uint32_t)G2_BK, 1};
+    int rc = make_tensor_map(&tmB, Wd, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 3, dims, strides, box, true);
+    if (rc) return rc;
+  }
+  Gemm2Args a;
+  glu_common_args(a, M, (I + 255) / 256, H, I, dgu, 2LL * I, const_cast<void*>(gu), 2LL * I);
+  return launch_gemm2<false, true, __nv_bfloat16, 256, 2>(tmA, tmB, a, stream);
+}
 
 // ---- grouped launch, host side --------------------------------------------------------------------
 // Problems are bf16-out, 256-wide-tile CTA-pair GEMMs (M > 128).  `k_splits` of a problem > 1 requests split-K
@@ -1051,6 +1302,9 @@ int gemm_bf16_2cta(bool a_mn, bool b_mn, int M, int N, int K, int batch, const v
   a.staged_epi = (staged_env != 0 && !(staged_env == 2 && symmetric) && !out_f32 && k_splits <= 1) ? 1 : 0;
   a.n_peers = n_peers;
   for (int i = 0; i < G2_MAX_PEERS; ++i) a.peer_D[i] = i < n_peers ? const_cast<void*>(peer_D[i]) : nullptr;
+  a.glu_I = 0;
+  a.aux = nullptr;
+  a.ld_aux = 0;
   int rc;
   if (!a_mn && !b_mn) rc = dispatch2<false, false>(out_f32, bn, tmA, tmB, a, stream);
   else if (!a_mn && b_mn) rc = dispatch2<false, true>(out_f32, bn, tmA, tmB, a, stream);

@@ -765,6 +765,84 @@ class _GluFn(torch.autograd.Function):
         return dg, du
 
 
+def _adjacent_rows(w_a: torch.Tensor, w_b: torch.Tensor) -> bool:
+    return (w_a.shape == w_b.shape and w_a.is_contiguous() and w_b.is_contiguous() and
+            w_b.data_ptr() == w_a.data_ptr() + w_a.numel() * w_a.element_size())
+
+
+class _MlpFn(torch.autograd.Function):
+    """down( gate(x) * sigmoid(up(x)) * 2 )  (arch/llama.py:142-151) with the activation inside the GEMM epilogues:
+
+      forward   [g | u], y = b200_mlp_gateup_glu_fwd(x, [Wg ; Wu])      one tcgen05 kernel (in-tree engine)
+                out        = y Wd^T                                      library GEMM
+      backward  dWd       += dout^T y                                    library GEMM into the flat gradient
+                [dg | du]  = b200_mlp_down_glu_bwd(dout, Wd, [g | u])    one tcgen05 kernel: dout Wd never leaves the chip
+                dx         = [dg | du] [Wg ; Wu]                         ONE library GEMM (K = 2I) instead of two
+                d[Wg ; Wu] += [dg | du]^T x                              ONE library GEMM into the flat gradient
+
+    Needs gate_proj.weight and up_proj.weight adjacent in memory (flat.ParamStore) with flat-buffer gradients,
+    bf16, intermediate size % 128 == 0; `mlp()` falls back to the unfused path otherwise."""
+
+    @staticmethod
+    def forward(ctx, x, wg, wu, wd):
+        I, K = wg.shape
+        x2 = x.reshape(-1, K).contiguous()
+        M = x2.shape[0]
+        gu = torch.empty((M, 2 * I), device=x.device, dtype=torch.bfloat16)
+        y = torch.empty((M, I), device=x.device, dtype=torch.bfloat16)
+        tok = _t0("mlp_glu_fwd")
+        check(lib().b200_mlp_gateup_glu_fwd(x2.data_ptr(), wg.data_ptr(), gu.data_ptr(), y.data_ptr(), M, K, I,
+                                            _stream()), "b200_mlp_gateup_glu_fwd")
+        _t1(tok)
+        out = y @ wd.t()
+        ctx.save_for_backward(x2, gu, y, wg, wu, wd)
+        ctx.x_shape = x.shape
+        return out.view(*x.shape[:-1], wd.shape[0])
+
+    @staticmethod
+    def backward(ctx, dout):
+        x2, gu, y, wg, wu, wd = ctx.saved_tensors
+        I, K = wg.shape
+        H = wd.shape[0]
+        M = x2.shape[0]
+        d2 = dout.reshape(-1, H).contiguous()
+        wd.grad.addmm_(d2.t(), y)                                   # dWd
+        dgu = torch.empty((M, 2 * I), device=d2.device, dtype=torch.bfloat16)
+        tok = _t0("mlp_glu_bwd")
+        check(lib().b200_mlp_down_glu_bwd(d2.data_ptr(), wd.data_ptr(), gu.data_ptr(), dgu.data_ptr(), M, H, I,
+                                          _stream()), "b200_mlp_down_glu_bwd")
+        _t1(tok)
+        w2 = torch.as_strided(wg, (2 * I, K), (K, 1))               # [Wg ; Wu], adjacent in the flat store
+        g2 = torch.as_strided(wg.grad, (2 * I, K), (K, 1))
+        dx = dgu @ w2 if ctx.needs_input_grad[0] else None
+        g2.addmm_(dgu.t(), x2)
+        return (dx.view(ctx.x_shape) if dx is not None else None), None, None, None
+
+
+def mlp_fusable(x: torch.Tensor, wg: torch.Tensor, wu: torch.Tensor, wd: torch.Tensor) -> bool:
+    if not (x.is_cuda and x.dtype == torch.bfloat16 and wg.dtype == torch.bfloat16 and wd.dtype == torch.bfloat16):
+        return False
+    if wg.shape[0] % 128 != 0 or wg.shape[1] % 8 != 0 or wd.shape != (wg.shape[1], wg.shape[0]) or not wd.is_contiguous():
+        return False
+    flat = all(getattr(w, "_b200_flat_grad", False) and w.grad is not None and w.grad.dtype == torch.bfloat16
+               for w in (wg, wu, wd))
+    return flat and _adjacent_rows(wg, wu) and _adjacent_rows(wg.grad, wu.grad)
+
+
+def mlp(x: torch.Tensor, wg: torch.Tensor, wu: torch.Tensor, wd: torch.Tensor) -> torch.Tensor:
+    """The reference MLP (arch/llama.py:149-151) on three bias-free projections."""
+    if mlp_fusable(x, wg, wu, wd) and _MLP_FUSED:
+        return _MlpFn.apply(x, wg, wu, wd)
+    g, u = multi_linear(x, (wg, wu))
+    return linear(glu(g, u), wd)
+
+
+import os as _os
+# B200_MLP_FUSED=0 restores the library GEMMs + elementwise GLU kernels (A/B switch for measurements; the first
+# version of the fused epilogues, with row-per-lane 16-byte stores, LOST to that pair -- see DESIGN.md section 4.6)
+_MLP_FUSED = _os.environ.get("B200_MLP_FUSED", "1") != "0"
+
+
 def glu(gate: torch.Tensor, up: torch.Tensor) -> torch.Tensor:
     """gate * sigmoid(up) * 2 (arch/llama.py:151).  bf16 tensors with numel % 8 == 0 take the fused
     kernel; other dtypes (fp32 configs) use the same formula through torch ops."""

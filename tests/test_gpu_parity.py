@@ -724,3 +724,47 @@ def test_attention_fp32_path_large_logits(ops, B, S, H, Hk, D):
     qb, kb, vb = (t.detach().to(torch.bfloat16).requires_grad_(True) for t in (q, k, v))
     ob = ops.attention(qb, kb, vb, D ** -0.5, True)
     assert rel(ob, orf) > 2 * errs[0], (rel(ob, orf), errs[0])
+
+
+@pytest.mark.parametrize("M,K,I", [(300, 128, 256), (1024, 1024, 2816), (515, 256, 384)])
+def test_mlp_fused_glu_epilogues(ops, M, K, I):
+    """The MLP block on the in-tree GEMM engine (b200_mlp_gateup_glu_fwd / b200_mlp_down_glu_bwd: gate*sigmoid(up)*2 and
+    its adjoint inside the tcgen05 epilogues, arch/llama.py:149-151) against fp32 autograd of the same formula, and
+    against the unfused path (library GEMMs + glu kernels)."""
+    torch.manual_seed(80 + I)
+    wflat = (torch.randn(2 * I * K, device="cuda") * K ** -0.5).to(torch.bfloat16)
+    gflat = torch.zeros_like(wflat)
+    ws = []
+    for i in range(2):
+        w = wflat[i * I * K:(i + 1) * I * K].view(I, K).requires_grad_(True)
+        w.grad = gflat[i * I * K:(i + 1) * I * K].view(I, K)
+        w._b200_flat_grad = True
+        ws.append(w)
+    wg, wu = ws
+    wd = (torch.randn(K, I, device="cuda") * I ** -0.5).to(torch.bfloat16).requires_grad_(True)
+    wd.grad = torch.zeros_like(wd)
+    wd._b200_flat_grad = True
+    x = torch.randn(2, M // 2 if M % 2 == 0 else M, K, device="cuda").to(torch.bfloat16)
+    x = x.reshape(-1, K)[:M].reshape(1, M, K).contiguous().requires_grad_(True)
+    assert ops.mlp_fusable(x, wg, wu, wd)
+    out = ops.mlp(x, wg, wu, wd)
+    dout = torch.randn_like(out)
+    out.backward(dout)
+    xr = x.detach().float().requires_grad_(True)
+    wr = [w.detach().float().requires_grad_(True) for w in (wg, wu, wd)]
+    lin = torch.nn.functional.linear
+    ref = lin(lin(xr, wr[0]) * torch.sigmoid(lin(xr, wr[1])) * 2, wr[2])
+    ref.backward(dout.float())
+    assert rel(out, ref) < 8e-3
+    assert rel(x.grad, xr.grad) < 1.2e-2
+    assert rel(gflat.view(2 * I, K), torch.cat([wr[0].grad, wr[1].grad])) < 1.2e-2
+    assert rel(wd.grad, wr[2].grad) < 8e-3
+    # raw entry points: [g | u] and y
+    gu = torch.empty(M, 2 * I, device="cuda", dtype=torch.bfloat16)
+    y = torch.empty(M, I, device="cuda", dtype=torch.bfloat16)
+    x2 = x.detach().reshape(M, K)
+    ops.check(ops.lib().b200_mlp_gateup_glu_fwd(x2.data_ptr(), wg.data_ptr(), gu.data_ptr(), y.data_ptr(), M, K, I,
+                                                ops._stream()), "fwd")
+    g_ref, u_ref = lin(x2.float(), wr[0].detach()), lin(x2.float(), wr[1].detach())
+    assert rel(gu[:, :I], g_ref) < 4e-3 and rel(gu[:, I:], u_ref) < 4e-3
+    assert rel(y, g_ref * torch.sigmoid(u_ref) * 2) < 4e-3
