@@ -219,6 +219,12 @@ int b200_mlp_down_glu_bwd(const void* dy, const void* Wd, const void* gu, void* 
 int b200_glu_fwd(const void* gate, const void* up, void* y, long long n, void* stream);
 int b200_glu_bwd(const void* dy, const void* gate, const void* up, void* dgate, void* dup, long long n,
                  void* stream);
+/* Adjoint of the embedding gather (arch/llama.py:389): grad[tokens[r], :] += dh[r, :] for r in [0, rows);
+ * dh bf16 [rows, H]; grad bf16 or f32 [V, H] (accumulated into: it may already hold the tied-logits wgrad);
+ * fp32 accumulation per vocabulary row in the workspace (V*H floats), tokens outside [0, V) are ignored. */
+size_t b200_embedding_bwd_workspace_bytes(int V, int H);
+int b200_embedding_bwd(const void* dh, const long long* tokens, void* grad, int grad_is_bf16, long long rows,
+                       int V, int H, void* workspace, size_t workspace_bytes, void* stream);
 /* core/training.py:1226-1234: per-row cross entropy of bf16 logits [rows, ld] (first V columns valid),
  * computed in fp32: row_lse = logsumexp, row_loss = (target != pad_token) ? lse - logit[target] : 0.
  * ce_bwd overwrites logits with row_scale[row] * (softmax - onehot(target)) (0 in columns >= V and in

@@ -54,6 +54,8 @@ SIGNATURES = {
     "b200_rope": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "b200_mlp_gateup_glu_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "b200_mlp_down_glu_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "b200_embedding_bwd_workspace_bytes": (_sz, [_i, _i]),
+    "b200_embedding_bwd": (_i, [_vp, _vp, _vp, _i, _ll, _i, _i, _vp, _sz, _vp]),
     "b200_glu_fwd": (_i, [_vp, _vp, _vp, _ll, _vp]),
     "b200_glu_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _ll, _vp]),
     "b200_ce_fwd": (_i, [_vp, _ll, _vp, _i, _i, _ll, _vp, _vp, _vp]),

@@ -152,7 +152,7 @@ class Model(nn.Module):
     def hidden_states(self, inputs: torch.Tensor, position_ids=None, attention_mask=None) -> torch.Tensor:
         B, S = inputs.shape
         mask = CausalMask(S) if attention_mask is None else attention_mask
-        h = self.embed_tokens(inputs)
+        h = ops.embedding(inputs, self.embed_tokens.weight)
         pending = None
         for layer in self.layers:
             h, pending = layer.forward_fused(h, pending, mask=mask, position_ids=position_ids)

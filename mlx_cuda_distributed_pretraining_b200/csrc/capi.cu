@@ -28,6 +28,9 @@ int newton_schulz_multi(const NsGroup* g, int n, int steps, float a, float b, fl
 int gemm_glu_fwd_2cta(const void* x, const void* W2, void* gu, void* y, int M, int K, int I, cudaStream_t stream);
 int gemm_glu_bwd_2cta(const void* dy, const void* Wd, const void* gu, void* dgu, int M, int H, int I,
                       cudaStream_t stream);
+size_t embedding_bwd_workspace_bytes(int V, int H);
+int embedding_bwd(const void* dh, const long long* tokens, void* grad, int grad_is_bf16, long long rows, int V, int H,
+                  void* ws, size_t ws_bytes, cudaStream_t stream);
 size_t reduce_workspace_bytes(int batch);
 int muon_momentum(const void* g, int g_is_bf16, float* buf, void* u_bf16, float* sumsq,
                   long long numel, int batch, float mu, int nesterov, float gscale, void* ws,
@@ -150,6 +153,11 @@ int b200_mlp_gateup_glu_fwd(const void* x, const void* W2, void* gu, void* y, in
 int b200_mlp_down_glu_bwd(const void* dy, const void* Wd, const void* gu, void* dgu, int M, int H, int I,
                           void* stream) {
   return b200::gemm_glu_bwd_2cta(dy, Wd, gu, dgu, M, H, I, S_(stream));
+}
+size_t b200_embedding_bwd_workspace_bytes(int V, int H) { return b200::embedding_bwd_workspace_bytes(V, H); }
+int b200_embedding_bwd(const void* dh, const long long* tokens, void* grad, int grad_is_bf16, long long rows,
+                       int V, int H, void* workspace, size_t workspace_bytes, void* stream) {
+  return b200::embedding_bwd(dh, tokens, grad, grad_is_bf16, rows, V, H, workspace, workspace_bytes, S_(stream));
 }
 size_t b200_reduce_workspace_bytes(int batch) { return b200::reduce_workspace_bytes(batch); }
 int b200_muon_momentum(const void* g, int g_is_bf16, float* buf, void* u_bf16, float* sumsq,

@@ -63,6 +63,56 @@ glu_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __rest
   }
 }
 
+// ---- embedding backward (adjoint of the gather in arch/llama.py:389, `h = self.embed_tokens(inputs)`) --------------
+// dW[token[t], :] += dh[t, :].  Two passes over a caller-provided fp32 scratch [V, H] (zeroed by the entry point):
+// (1) one warp per token row scatters its bf16 gradient row with fp32 red.global (rows hit by many tokens -- a 259-entry
+// byte vocabulary sees hundreds of hits per row -- accumulate in fp32, not in the bf16 gradient buffer), (2) the scratch
+// is added into the gradient (which already holds the tied-logits wgrad) in one vectorised pass.
+__global__ void __launch_bounds__(256)
+embedding_scatter_kernel(const __nv_bfloat16* __restrict__ dh, const long long* __restrict__ tokens,
+                         float* __restrict__ scratch, long long rows, int H, int V) {
+  const int lane = threadIdx.x & 31;
+  for (long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); r < rows; r += (long long)gridDim.x * 8) {
+    const long long tok = tokens[r];
+    if (tok < 0 || tok >= V) continue;
+    const __nv_bfloat16* src = dh + r * H;
+    float* dst = scratch + tok * H;
+    for (int c = lane * 8; c < H; c += 256) {
+      float f[8];
+      ld8f(src + c, f);
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + c), "f"(f[0]), "f"(f[1]), "f"(f[2]),
+                   "f"(f[3])
+                   : "memory");
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + c + 4), "f"(f[4]), "f"(f[5]), "f"(f[6]),
+                   "f"(f[7])
+                   : "memory");
+    }
+  }
+}
+
+template <typename G>
+__global__ void __launch_bounds__(256)
+embedding_accumulate_kernel(const float* __restrict__ scratch, G* __restrict__ grad, long long nvec) {
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < nvec; i += (long long)gridDim.x * 256) {
+    const float4 a = *reinterpret_cast<const float4*>(scratch + i * 8);
+    const float4 b = *reinterpret_cast<const float4*>(scratch + i * 8 + 4);
+    if constexpr (sizeof(G) == 2) {
+      float g[8];
+      ld8f(reinterpret_cast<const __nv_bfloat16*>(grad) + i * 8, g);
+      g[0] += a.x; g[1] += a.y; g[2] += a.z; g[3] += a.w;
+      g[4] += b.x; g[5] += b.y; g[6] += b.z; g[7] += b.w;
+      st8f(reinterpret_cast<__nv_bfloat16*>(grad) + i * 8, g);
+    } else {
+      float4* gp = reinterpret_cast<float4*>(grad) + i * 2;
+      float4 g0 = gp[0], g1 = gp[1];
+      g0.x += a.x; g0.y += a.y; g0.z += a.z; g0.w += a.w;
+      g1.x += b.x; g1.y += b.y; g1.z += b.z; g1.w += b.w;
+      gp[0] = g0;
+      gp[1] = g1;
+    }
+  }
+}
+
 constexpr int CE_THREADS = 512;
 
 // one CTA per row; online (max, sum) per thread, then a block reduction of the pairs
@@ -175,6 +225,36 @@ int glu_bwd(const void* dy, const void* g, const void* u, void* dg, void* du, lo
   glu_bwd_kernel<<<grid_for(n / 8), 256, 0, stream>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)g,
                                                      (const __nv_bfloat16*)u, (__nv_bfloat16*)dg,
                                                      (__nv_bfloat16*)du, n / 8);
+  B200_CHECK_LAUNCH();
+  return B200_OK;
+}
+
+size_t embedding_bwd_workspace_bytes(int V, int H) { return (size_t)V * H * sizeof(float); }
+
+int embedding_bwd(const void* dh, const long long* tokens, void* grad, int grad_is_bf16, long long rows, int V, int H,
+                  void* ws, size_t ws_bytes, cudaStream_t stream) {
+  B200_CHECK_ARG(rows > 0 && V > 0 && H > 0 && H % 8 == 0, "embedding_bwd: bad shape rows=%lld V=%d H=%d", rows, V, H);
+  if (ws == nullptr || ws_bytes < embedding_bwd_workspace_bytes(V, H)) {
+    set_error("embedding_bwd: workspace too small (%zu < %zu)", ws_bytes, embedding_bwd_workspace_bytes(V, H));
+    return B200_ERR_WORKSPACE;
+  }
+  B200_CHECK_ARG((reinterpret_cast<uintptr_t>(ws) & 15u) == 0 && (reinterpret_cast<uintptr_t>(grad) & 15u) == 0 &&
+                     (reinterpret_cast<uintptr_t>(dh) & 15u) == 0,
+                 "embedding_bwd: buffers must be 16-byte aligned");
+  float* scratch = reinterpret_cast<float*>(ws);
+  B200_CHECK_CUDA(cudaMemsetAsync(scratch, 0, (size_t)V * H * sizeof(float), stream));
+  long long blocks = (rows + 7) / 8;
+  const long long cap = (long long)num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  embedding_scatter_kernel<<<(int)blocks, 256, 0, stream>>>((const __nv_bfloat16*)dh, tokens, scratch, rows, H, V);
+  B200_CHECK_LAUNCH();
+  const long long nvec = (long long)V * H / 8;
+  long long b2 = (nvec + 255) / 256;
+  if (b2 > cap) b2 = cap;
+  if (grad_is_bf16)
+    embedding_accumulate_kernel<__nv_bfloat16><<<(int)b2, 256, 0, stream>>>(scratch, (__nv_bfloat16*)grad, nvec);
+  else
+    embedding_accumulate_kernel<float><<<(int)b2, 256, 0, stream>>>(scratch, (float*)grad, nvec);
   B200_CHECK_LAUNCH();
   return B200_OK;
 }

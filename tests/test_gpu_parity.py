@@ -768,3 +768,21 @@ def test_mlp_fused_glu_epilogues(ops, M, K, I):
     g_ref, u_ref = lin(x2.float(), wr[0].detach()), lin(x2.float(), wr[1].detach())
     assert rel(gu[:, :I], g_ref) < 4e-3 and rel(gu[:, I:], u_ref) < 4e-3
     assert rel(y, g_ref * torch.sigmoid(u_ref) * 2) < 4e-3
+
+
+@pytest.mark.parametrize("V,H,rows", [(259, 128, 4096), (32003, 1024, 16384), (67, 64, 24)])
+def test_embedding_backward_scatter(ops, V, H, rows):
+    """b200_embedding_bwd == index_add of the output gradient rows into the (already populated) weight gradient;
+    rows hit hundreds of times (byte vocabulary) are accumulated in fp32."""
+    torch.manual_seed(90 + V)
+    w = (torch.randn(V, H, device="cuda") * 0.1).to(torch.bfloat16).requires_grad_(True)
+    prior = (torch.randn(V, H, device="cuda") * 0.05).to(torch.bfloat16)   # e.g. the tied-logits wgrad
+    w.grad = prior.clone()
+    w._b200_flat_grad = True
+    tok = torch.randint(0, V, (rows,), device="cuda")
+    h = ops.embedding(tok.view(1, -1), w)
+    assert torch.equal(h[0], w.detach()[tok])
+    dh = torch.randn_like(h)
+    h.backward(dh)
+    ref = prior.float().index_add(0, tok, dh[0].float())
+    assert rel(w.grad, ref) < 4e-3
