@@ -28,6 +28,11 @@ int launch_attn_bwd64(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUte
                       void* dv, int B, int S, int H, int Hk, int dkv_row_heads, float scale, int causal,
                       cudaStream_t stream);
 
+int launch_attn_bwd128(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV,
+                       const CUtensorMap& tmDO, const float* lse, const float* delta, float* dq_acc, void* dk,
+                       void* dv, int B, int S, int H, int Hk, int dkv_row_heads, float scale, int causal,
+                       cudaStream_t stream);
+
 namespace {
 
 constexpr int BWD_THREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2-9: two softmax warpgroups
@@ -509,10 +514,13 @@ int attn_bwd(const void* q, const void* k, const void* v, const void* o, const v
     const char* e = getenv("B200_ATTN_BWD_V1");
     return e != nullptr && e[0] == '1';
   }();
-  const bool pipelined64 = D == 64 && !force_v1;
-  if (pipelined64)  // software-pipelined head_dim-64 kernel (attention_bwd64.cu)
+  const bool pipelined = !force_v1;   // software-pipelined kernels (attention_bwd64.cu / attention_bwd128.cu)
+  if (pipelined && D == 64)
     rc = launch_attn_bwd64(tmQ, tmK, tmV, tmDO, lse, delta, dq_acc, dk, dv, B, S, H, Hk, dkv_row_heads, scale, causal,
                            stream);
+  else if (pipelined)
+    rc = launch_attn_bwd128(tmQ, tmK, tmV, tmDO, lse, delta, dq_acc, dk, dv, B, S, H, Hk, dkv_row_heads, scale, causal,
+                            stream);
   else
     rc = D == 64 ? launch_bwd<64>(tmQ, tmK, tmV, tmDO, a, stream) : launch_bwd<128>(tmQ, tmK, tmV, tmDO, a, stream);
   if (rc) return rc;
@@ -520,9 +528,9 @@ int attn_bwd(const void* q, const void* k, const void* v, const void* o, const v
     const long long nvec = n / 8;
     long long blocks = (nvec + 255) / 256;
     if (blocks > (long long)num_sms() * 8) blocks = (long long)num_sms() * 8;
-    // the pipelined kernel accumulates dS without the softmax scale (one multiply less per score): applied here
+    // the pipelined kernels accumulate dS without the softmax scale (one multiply less per score): applied here
     f32_to_bf16_kernel<<<(int)blocks, 256, 0, stream>>>(dq_acc, reinterpret_cast<__nv_bfloat16*>(dq), nvec,
-                                                        pipelined64 ? scale : 1.0f);
+                                                        pipelined ? scale : 1.0f);
     B200_CHECK_LAUNCH();
   }
   return B200_OK;
