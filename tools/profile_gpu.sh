@@ -10,7 +10,7 @@ R=${1:-r02}
 MODE=${2:-all}   # launches | step | extra | attn | all
 mkdir -p gpurun_out
 B="python bench.py --warmup 3 --no-cpu-baseline --no-configs-block --no-e2e"
-MINE='regex:gemm2_|gemm_bf16_tc|splitk_|attn_|f32_to_bf16|muon_momentum|ns_scales|axpy_update|sgd_momentum|rmsnorm|glu_|ce_fwd|ce_bwd|clip_accum'
+MINE='regex:gemm2_|gemm_bf16_tc|splitk_|attn_|f32_to_bf16|muon_momentum|ns_scales|axpy_update|sgd_momentum|rmsnorm|glu_|ce_fwd|ce_bwd|clip_accum|embedding_'
 if [ "$MODE" = launches ] || [ "$MODE" = all ]; then
   ncu --metrics gpu__time_duration.sum --clock-control none -c 30000 --csv \
       --log-file gpurun_out/${R}_bench_launches.csv $B --steps 2 > gpurun_out/${R}_bench_under_ncu.log 2>&1
@@ -51,6 +51,10 @@ if [ "$MODE" = attn ] || [ "$MODE" = all ]; then
       -o gpurun_out/${R}_prof_attn_fwd $B --steps 1 > gpurun_out/${R}_prof_attn_fwd.log 2>&1
   ncu --set full --clock-control none --import-source on -k regex:attn_bwd64_kernel -s 36 -c 1 -f \
       -o gpurun_out/${R}_prof_attn_bwd $B --steps 1 > gpurun_out/${R}_prof_attn_bwd.log 2>&1
+  ncu --set full --clock-control none --import-source on -k regex:attn_bwd128_kernel -s 48 -c 1 -f \
+      -o gpurun_out/${R}_prof_attn_bwd128 python bench.py --config c5 --steps 1 --warmup 3 --no-cpu-baseline --no-e2e \
+      > gpurun_out/${R}_prof_attn_bwd128.log 2>&1
+  ncu -i gpurun_out/${R}_prof_attn_bwd128.ncu-rep --page raw --csv > gpurun_out/${R}_attn_bwd128_full.csv 2>/dev/null
   echo "attention source captures done"
 fi
 ls -la gpurun_out | tail -12

@@ -24,7 +24,7 @@ HBM = float(PEAKS.get("hbm_gbs", 6575.1))
 
 MINE = ("gemm_bf16_tc", "gemm2_", "splitk_", "delta_kernel", "attn_", "rmsnorm", "rope_kernel", "muon_", "axpy", "adamw",
         "clip_accum", "sumsq", "ns_scales", "sgd_momentum", "f32_to_bf16", "ema_split", "graft_", "split_bf16", "split4",
-        "root_", "glu_", "ce_", "adam_direction")
+        "root_", "glu_", "ce_", "adam_direction", "embedding_")
 
 
 def short(name: str) -> str:
@@ -87,7 +87,8 @@ def kernel_tables():
           "clock-unlocked (compare ratios, not absolutes).", ""]
     traffic = None
     for tag, title in (("step_full", "one C2 step"), ("adamw_full", "AdamW (C5, 1B parameters, one flat launch)"),
-                       ("shampoo_full", "Shampoo elementwise kernels (C4)")):
+                       ("shampoo_full", "Shampoo elementwise kernels (C4)"),
+                       ("attn_bwd128_full", "attention backward, head dim 128 (one C5 layer call)")):
         p = GP / f"{R}_{tag}.csv"
         if not p.exists():
             continue
