@@ -16,8 +16,10 @@
 //               row max moved.
 // The S accumulator is handed back as soon as the scores sit in registers, so QK^T(j+1) overlaps the
 // exponentials of tile j even with a single S buffer.
-#include <stdlib.h>
-
+// Tried in r02 and dropped (commit "attention forward: register-prefetch variant"): one CTA per SM with S double-buffered
+// in TMEM and a second set of 64 score registers per thread, so that tile j+1's scores stream out of tensor memory
+// (asynchronous tcgen05.ld) under tile j's exponentials.  Correct, but slower everywhere: 137 vs 97 us (S=1024, D=64),
+// 397 vs 277 us (S=2048), 1023 vs 863 us (D=128, C5 shape) -- the second resident CTA hides more than the prefetch does.
 #include "common.cuh"
 #include "host.h"
 
@@ -33,7 +35,6 @@ constexpr int KV_STAGES = 2;
 // of tcgen05.mma (A in TMEM, B = V in smem): no 32 KB smem round trip per key tile, and the MMA reads only V
 // from shared memory.  false = the first version (P as a swizzled K-major smem tile).
 constexpr bool kPInTmem = true;
-constexpr bool kFwdPfDefault[2] = {false, false};  // {head dim 64, head dim 128}: set from the measured A/B
 
 template <int D>
 struct FwdCfg {
@@ -353,316 +354,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   }
 }
 
-// ------------------------------------------------------------------------------------------------------
-// r02: register-prefetch variant (one CTA per SM).  The kernel above alternates, per key tile, a TMEM-read-bound
-// phase (the scores: 64 KB per tile at 64 B/clk/SM = 1024 cycles) and a MUFU-bound phase (16 384 exponentials at
-// 16/clk/SM = 1024 cycles), and both softmax warpgroups of a CTA meet at a named barrier every tile, so the two phases
-// ADD; a second resident CTA only overlaps them by chance (ncu: tensor pipe 22 %, XU pipe 46 %).  Here a thread keeps
-// TWO sets of score registers: while the exponentials of tile j run, the scores of tile j+1 are already streaming
-// out of tensor memory (tcgen05.ld is asynchronous until tcgen05.wait::ld).  That needs S^T double-buffered in TMEM
-// (S(j+1) must be complete while tile j is still being processed) and ~170 registers per thread, hence one CTA per
-// SM: TMEM S 2x128 | O D | P 64.
-// ------------------------------------------------------------------------------------------------------
-template <int D>
-struct FwdPfCfg {
-  static constexpr int TILE_BYTES = 128 * D * 2;
-  static constexpr int OFF_Q = 0;
-  static constexpr int OFF_K = OFF_Q + TILE_BYTES;
-  static constexpr int OFF_V = OFF_K + KV_STAGES * TILE_BYTES;
-  static constexpr int OFF_BAR = OFF_V + 2 * TILE_BYTES;
-  static constexpr int OFF_RED = OFF_BAR + 256;
-  static constexpr int SMEM_BYTES = OFF_RED + 3072 + 1024;
-  static constexpr int TM_S = 0, TM_O = 256, TM_P = 256 + D;  // S buffers at 0 and 128
-  static constexpr int TMEM_COLS = 512;
-};
-
-// the 64 prefetched score registers must not be consumed before tcgen05.wait::ld: route them through (empty) volatile
-// asm statements placed after the wait, which the compiler may not reorder with it
-__device__ __forceinline__ void reg_fence64(uint32_t* v) {
-#pragma unroll
-  for (int i = 0; i < 64; i += 16)
-    asm volatile("" : "+r"(v[i + 0]), "+r"(v[i + 1]), "+r"(v[i + 2]), "+r"(v[i + 3]), "+r"(v[i + 4]), "+r"(v[i + 5]),
-                      "+r"(v[i + 6]), "+r"(v[i + 7]), "+r"(v[i + 8]), "+r"(v[i + 9]), "+r"(v[i + 10]), "+r"(v[i + 11]),
-                      "+r"(v[i + 12]), "+r"(v[i + 13]), "+r"(v[i + 14]), "+r"(v[i + 15]));
-}
-
-template <int D>
-__global__ void __launch_bounds__(FWD_THREADS, 1)
-attn_fwd_pf_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                   const __grid_constant__ CUtensorMap tmV, const FwdArgs p) {
-  using Cfg = FwdPfCfg<D>;
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t sQ = sbase + Cfg::OFF_Q;
-  auto sK = [&](int st) { return sbase + Cfg::OFF_K + st * Cfg::TILE_BYTES; };
-  auto sV = [&](int j) { return sbase + Cfg::OFF_V + (j & 1) * Cfg::TILE_BYTES; };
-  const uint32_t bar = sbase + Cfg::OFF_BAR;
-  const uint32_t q_full = bar;
-  auto k_full = [&](int s) { return bar + 8u * (1 + s); };
-  auto k_empty = [&](int s) { return bar + 8u * (3 + s); };
-  auto v_full = [&](int j) { return bar + 8u * (5 + (j & 1)); };
-  auto v_empty = [&](int j) { return bar + 8u * (7 + (j & 1)); };
-  auto s_full = [&](int j) { return bar + 8u * (9 + (j & 1)); };
-  auto s_empty = [&](int j) { return bar + 8u * (11 + (j & 1)); };
-  const uint32_t p_full = bar + 8u * 13;
-  const uint32_t pv_done = bar + 8u * 14;
-  const uint32_t tmem_slot = bar + 8u * 15;
-  float* red_s = reinterpret_cast<float*>(smem_raw + (sbase - smem_u32(smem_raw)) + Cfg::OFF_RED);
-
-  const int warp = warp_idx_uniform();
-  const int lane = threadIdx.x & 31;
-  const int qt = (int)gridDim.x - 1 - (int)blockIdx.x;  // heaviest (longest causal row) tiles first
-  const int h = blockIdx.y;
-  const int b = blockIdx.z;
-  const int hk = h / (p.H / p.Hk);
-  const int q0 = qt * ATT_BQ;
-  const int n_kv_all = (p.S + ATT_BKV - 1) / ATT_BKV;
-  const int n_kv = p.causal ? (qt + 1 < n_kv_all ? qt + 1 : n_kv_all) : n_kv_all;
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmQ);
-    tma_prefetch_desc(&tmK);
-    tma_prefetch_desc(&tmV);
-  }
-  if (warp == 1 && lane == 0) {
-    mbar_init(q_full, 1);
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(k_full(s), 1);
-      mbar_init(k_empty(s), 1);
-      mbar_init(v_full(s), 1);
-      mbar_init(v_empty(s), 1);
-      mbar_init(s_full(s), 1);
-      mbar_init(s_empty(s), 8);
-    }
-    mbar_init(p_full, 8);
-    mbar_init(pv_done, 1);
-    fence_mbar_init();
-  }
-  if (warp == 2) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
-  tc_fence_before_sync();
-  __syncthreads();
-  tc_fence_after_sync();
-  uint32_t tmem_base;
-  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
-
-  if (warp == 0) {
-    if (lane == 0) {
-      mbar_arrive_expect_tx(q_full, Cfg::TILE_BYTES);
-#pragma unroll
-      for (int db = 0; db < D / 64; ++db) tma_load_4d(sQ + db * 16384, &tmQ, q_full, db * 64, h, q0, b);
-      for (int j = 0; j < n_kv; ++j) {
-        const int st = j & 1;
-        const uint32_t ph = (j >> 1) & 1u;
-        mbar_wait(k_empty(st), ph ^ 1u);
-        mbar_arrive_expect_tx(k_full(st), Cfg::TILE_BYTES);
-#pragma unroll
-        for (int db = 0; db < D / 64; ++db)
-          tma_load_4d(sK(st) + db * 16384, &tmK, k_full(st), db * 64, hk, j * ATT_BKV, b);
-        mbar_wait(v_empty(j), ph ^ 1u);
-        mbar_arrive_expect_tx(v_full(j), Cfg::TILE_BYTES);
-#pragma unroll
-        for (int db = 0; db < D / 64; ++db)
-          tma_load_4d(sV(j) + db * 16384, &tmV, v_full(j), db * 64, hk, j * ATT_BKV, b);
-      }
-    }
-  } else if (warp == 1) {
-    constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, false, false);
-    constexpr uint32_t idesc_pv = make_idesc_bf16(128, D, false, true);
-    auto issue_s = [&](int j) {  // S(j) into buffer j & 1
-      const int st = j & 1;
-      const uint32_t ph = (j >> 1) & 1u;
-      mbar_wait(s_empty(j), ph ^ 1u);  // the scores of tile j-2 have left this buffer
-      mbar_wait(k_full(st), ph);
-      tc_fence_after_sync();
-      if (elect_one()) {
-#pragma unroll
-        for (int kk = 0; kk < D / 16; ++kk) {
-          const uint32_t off = (kk >> 2) * 16384 + (kk & 3) * 32;
-          umma_bf16_ss(tmem_base + Cfg::TM_S + st * 128, make_smem_desc_sw128(sQ + off, 0, 1024),
-                       make_smem_desc_sw128(sK(st) + off, 0, 1024), idesc_s, kk != 0);
-        }
-        umma_commit(k_empty(st));
-        umma_commit(s_full(j));
-      }
-      __syncwarp();
-    };
-    mbar_wait(q_full, 0);
-    issue_s(0);
-    if (n_kv > 1) issue_s(1);
-    for (int j = 0; j < n_kv; ++j) {
-      // S(j+2) goes into the buffer tile j's scores are leaving (prefetched during softmax(j-1)): it is issued a whole
-      // iteration before softmax(j+1) asks for it
-      if (j + 2 < n_kv) issue_s(j + 2);
-      mbar_wait(p_full, j & 1u);
-      mbar_wait(v_full(j), (j >> 1) & 1u);
-      tc_fence_after_sync();
-      if (elect_one()) {
-#pragma unroll
-        for (int kk = 0; kk < ATT_BKV / 16; ++kk)
-          umma_bf16_ts(tmem_base + Cfg::TM_O, tmem_base + Cfg::TM_P + kk * 8,
-                       make_smem_desc_sw128(sV(j) + kk * 2048, 16384, 1024), idesc_pv, (j | kk) != 0);
-        umma_commit(v_empty(j));
-        umma_commit(pv_done);
-      }
-      __syncwarp();
-    }
-  } else {
-    // ------------------------------------ softmax warps -------------------------------------
-    const int qd = warp & 3;
-    const int wg = (warp - 2) >> 2;
-    const int row = qd * 32 + lane;
-    const int q_row = q0 + row;
-    const uint32_t t_lane = tmem_base + (uint32_t(qd * 32) << 16);
-    const float sl2 = p.scale * 1.4426950408889634f;
-    const int cbase = wg * 64;
-    constexpr int OH = D / 2;
-    float m = -INFINITY, l = 0.f;
-    const int kmax = p.causal ? (q_row < p.S - 1 ? q_row : p.S - 1) : p.S - 1;  // last valid key
-
-    // one key tile: `cur` holds its scores (already waited for), `nxt` receives tile j+1's asynchronously
-    auto tile = [&](int j, uint32_t* cur, uint32_t* nxt) {
-      const int k0 = j * ATT_BKV + cbase;
-      const bool need_mask = (p.causal && j * ATT_BKV + ATT_BKV - 1 > q0) || (j * ATT_BKV + ATT_BKV > p.S);
-      float mx = -INFINITY;
-      if (need_mask) {
-#pragma unroll
-        for (int i = 0; i < 64; ++i) {
-          if (k0 + i > kmax) cur[i] = __float_as_uint(-INFINITY);
-          mx = fmaxf(mx, __uint_as_float(cur[i]));
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < 64; ++i) mx = fmaxf(mx, __uint_as_float(cur[i]));
-      }
-      float* mslot = red_s + (j & 1) * 256;
-      mslot[wg * 128 + row] = mx;
-      named_bar_sync(1, 256);
-      mx = fmaxf(mx, mslot[(wg ^ 1) * 128 + row]);
-      const float m_new = fmaxf(m, mx);
-      const float alpha = fast_exp2((m - m_new) * sl2);
-      const float mb = m_new * sl2;
-      // O accumulator and P buffer are free once PV(j-1) has retired; the (rare) rescale of O comes BEFORE the prefetch
-      // is issued, because its tcgen05.wait::ld would also wait for the prefetch
-      if (j > 0) {
-        mbar_wait(pv_done, (j - 1) & 1u);
-        tc_fence_after_sync();
-        if (__any_sync(0xffffffffu, m_new > m)) {
-#pragma unroll 1
-          for (int c0 = 0; c0 < OH; c0 += 8) {
-            uint32_t o[8];
-            tmem_ld_32x32b_x8(t_lane + Cfg::TM_O + wg * OH + c0, o);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 8; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            tmem_st_32x32b_x8(t_lane + Cfg::TM_O + wg * OH + c0, o);
-          }
-          tmem_st_wait();
-        }
-      }
-      // prefetch: tile j+1's scores start leaving tensor memory now and arrive under the exponentials below
-      if (j + 1 < n_kv) {
-        mbar_wait(s_full(j + 1), ((j + 1) >> 1) & 1u);
-        tc_fence_after_sync();
-        const uint32_t t_s = t_lane + Cfg::TM_S + ((j + 1) & 1) * 128 + cbase;
-        tmem_ld_32x32b_x32(t_s, nxt);
-        tmem_ld_32x32b_x32(t_s + 32, nxt + 32);
-      }
-      float rs = 0.f;
-#pragma unroll
-      for (int hlf = 0; hlf < 2; ++hlf) {
-        uint32_t pk[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float e0 = fast_exp2(fmaf(__uint_as_float(cur[hlf * 32 + 2 * i]), sl2, -mb));
-          const float e1 = fast_exp2(fmaf(__uint_as_float(cur[hlf * 32 + 2 * i + 1]), sl2, -mb));
-          rs += e0 + e1;
-          pk[i] = pack_bf16x2(e0, e1);
-        }
-        tmem_st_32x32b_x16(t_lane + Cfg::TM_P + wg * 32 + hlf * 16, pk);
-      }
-      tmem_st_wait();
-      l = l * alpha + rs;
-      m = m_new;
-      tc_fence_before_sync();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(p_full);
-      if (j + 1 < n_kv) {
-        tmem_ld_wait();
-        reg_fence64(nxt);
-        tc_fence_before_sync();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(s_empty(j + 1));  // S buffer (j+1)&1 may take tile j+3
-      }
-    };
-
-    uint32_t va[64], vb[64];
-    mbar_wait(s_full(0), 0);
-    tc_fence_after_sync();
-    tmem_ld_32x32b_x32(t_lane + Cfg::TM_S + cbase, va);
-    tmem_ld_32x32b_x32(t_lane + Cfg::TM_S + cbase + 32, va + 32);
-    tmem_ld_wait();
-    tc_fence_before_sync();
-    __syncwarp();
-    if (lane == 0) mbar_arrive(s_empty(0));
-#pragma unroll 1
-    for (int j = 0; j < n_kv; j += 2) {
-      tile(j, va, vb);
-      if (j + 1 < n_kv) tile(j + 1, vb, va);
-    }
-
-    // --------------------------------------- epilogue ---------------------------------------
-    float* lslot = red_s + 512;
-    lslot[wg * 128 + row] = l;
-    named_bar_sync(1, 256);
-    l += lslot[(wg ^ 1) * 128 + row];
-    mbar_wait(pv_done, (n_kv - 1) & 1u);
-    tc_fence_after_sync();
-    const float inv_l = 1.0f / l;
-    __nv_bfloat16* orow = p.o + (((long long)b * p.S + q_row) * p.H + h) * D + wg * OH;
-#pragma unroll 1
-    for (int c0 = 0; c0 < OH; c0 += 32) {
-      uint32_t o[32];
-      tmem_ld_32x32b_x32(t_lane + Cfg::TM_O + wg * OH + c0, o);
-      tmem_ld_wait();
-      if (q_row < p.S) {
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          uint4 o4;
-          o4.x = pack_bf16x2(__uint_as_float(o[g * 8 + 0]) * inv_l, __uint_as_float(o[g * 8 + 1]) * inv_l);
-          o4.y = pack_bf16x2(__uint_as_float(o[g * 8 + 2]) * inv_l, __uint_as_float(o[g * 8 + 3]) * inv_l);
-          o4.z = pack_bf16x2(__uint_as_float(o[g * 8 + 4]) * inv_l, __uint_as_float(o[g * 8 + 5]) * inv_l);
-          o4.w = pack_bf16x2(__uint_as_float(o[g * 8 + 6]) * inv_l, __uint_as_float(o[g * 8 + 7]) * inv_l);
-          stg128(orow + c0 + g * 8, o4);
-        }
-      }
-    }
-    if (wg == 0 && q_row < p.S) p.lse[((long long)b * p.H + h) * p.S + q_row] = m * p.scale + logf(l);
-  }
-
-  tc_fence_before_sync();
-  __syncthreads();
-  if (warp == 2) {
-    tc_fence_after_sync();
-    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
-  }
-}
-
-template <int D>
-int launch_fwd_pf(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV, const FwdArgs& a,
-                  cudaStream_t stream) {
-  using Cfg = FwdPfCfg<D>;
-  auto kern = attn_fwd_pf_kernel<D>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    B200_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_set = true;
-  }
-  dim3 grid((a.S + ATT_BQ - 1) / ATT_BQ, a.H, a.B);
-  kern<<<grid, FWD_THREADS, Cfg::SMEM_BYTES, stream>>>(tmQ, tmK, tmV, a);
-  B200_CHECK_LAUNCH();
-  return B200_OK;
-}
-
 template <int D>
 int launch_fwd(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV,
                const FwdArgs& a, cudaStream_t stream) {
@@ -712,13 +403,6 @@ int attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse, i
   a.Hk = Hk;
   a.scale = scale;
   a.causal = causal;
-  // B200_ATTN_FWD_PF: 0 = two-CTA kernel, 1 = register-prefetch kernel, unset = per head dim default
-  static const int pf_env = [] {
-    const char* e = getenv("B200_ATTN_FWD_PF");
-    return (e != nullptr && (e[0] == '0' || e[0] == '1')) ? e[0] - '0' : -1;
-  }();
-  const bool pf = pf_env >= 0 ? pf_env == 1 : kFwdPfDefault[D == 64 ? 0 : 1];
-  if (pf) return D == 64 ? launch_fwd_pf<64>(tmQ, tmK, tmV, a, stream) : launch_fwd_pf<128>(tmQ, tmK, tmV, a, stream);
   return D == 64 ? launch_fwd<64>(tmQ, tmK, tmV, a, stream) : launch_fwd<128>(tmQ, tmK, tmV, a, stream);
 }
 
