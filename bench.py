@@ -172,23 +172,27 @@ def load_peaks() -> dict:
 # ------------------------------------------------------------------------------------------------
 # CPU baseline: the oracle port of the reference step on the host cores
 # ------------------------------------------------------------------------------------------------
-def pick_cpu_threads() -> int:
-    """All host threads unless a quick sweep says fewer is faster (MKL/oneDNN oversubscription on SMT boxes):
-    times one 2048^3 fp32 matmul at n, n/2, n/4 threads and keeps the fastest.  The choice is reported in
-    cpu_baseline.cores."""
+def pick_cpu_threads(c: dict) -> int:
+    """Thread count for the CPU arm: the fastest of n, n/2, n/4, n/8 host threads on a probe of the workload itself
+    -- fwd+bwd of ONE sequence through a 2-layer cut of the config's model (same widths, seq <= 1024) -- because the
+    oracle's step mixes GEMMs with memory-bound elementwise work and a plain matmul probe picked 64 threads on a box
+    where 32 ran the real step 1.4x faster (profiles/r03_bench_c2.json vs r03_bench_reference.json).  The choice is
+    reported in cpu_baseline.cores."""
+    from oracle import reference_math as R
     n = os.cpu_count() or 1
-    cand = sorted({n, max(1, n // 2), max(1, n // 4)}, reverse=True)
-    a = torch.randn(2048, 2048)
+    cand = sorted({n, max(1, n // 2), max(1, n // 4), max(1, n // 8)}, reverse=True)
+    dims = R.LlamaDims(c["hidden"], c["inter"], 2, c["heads"], c["kv_heads"], c["head_dim"], c["vocab"])
+    params = R.init_params(dims, seed=1)
+    batch = R.synthetic_batch(0, 0, 1, min(c["seq"], 1024), c["vocab_normal"])
     best, best_t = n, float("inf")
-    for c in cand:
-        torch.set_num_threads(c)
-        a @ a
+    for th in cand:
+        torch.set_num_threads(th)
+        R.loss_and_grads(params, batch, dims, pad_token=c["vocab_normal"])       # warm the pool at this width
         t0 = time.perf_counter()
-        for _ in range(3):
-            a @ a
+        R.loss_and_grads(params, batch, dims, pad_token=c["vocab_normal"])
         t = time.perf_counter() - t0
-        if t < best_t * 0.95:     # prefer MORE threads unless fewer is clearly (5 %) faster
-            best, best_t = c, t
+        if t < best_t:
+            best, best_t = th, t
     torch.set_num_threads(best)
     return best
 
@@ -264,7 +268,7 @@ def run_reference(args) -> None:
     tag = args.config
     c = dims_of(load_config(tag, False))
     full = tag in ("c1", "c2")
-    threads = pick_cpu_threads()
+    threads = pick_cpu_threads(c)
     budget_s = float(os.environ.get("B200_BENCH_CPU_BUDGET_S", "150"))
     t_start = time.perf_counter()
     rows = []
@@ -584,7 +588,7 @@ def main() -> None:
         line["dp_check"] = r["dp_check"]
     if world == 1 and not args.no_cpu_baseline:
         try:
-            threads = pick_cpu_threads()
+            threads = pick_cpu_threads(dims_of(load_config(tag, False)))
             line["cpu_baseline"] = cpu_reference_step(tag, threads, full=tag in ("c1", "c2"))
             line["cpu_baseline"]["host_threads_available"] = os.cpu_count()
         except Exception as e:  # noqa: BLE001

@@ -786,3 +786,34 @@ def test_embedding_backward_scatter(ops, V, H, rows):
     h.backward(dh)
     ref = prior.float().index_add(0, tok, dh[0].float())
     assert rel(w.grad, ref) < 4e-3
+
+
+def test_shampoo_root_and_precondition_at_c4_size(ops):
+    """BASELINE C4 shapes: the [1024, 1024] Kronecker factors of a [2816, 1024] parameter (max_preconditioner_dim
+    1024), batched.  Statistics from bf16 gradients -> roots -> PL m PR against the oracle in fp64/fp32 on the host;
+    same 1e-4 (root) / 2e-4 (two chained bf16x3 products) bounds as the small golden cases."""
+    torch.manual_seed(95)
+    b, rows, cols, k = 2, 2816, 1024, 1024
+    G = (torch.randn(b, rows, cols) * 0.02).to(torch.bfloat16)
+    Gc = G.cuda()
+    L = torch.zeros(b, k, k, device="cuda")
+    Rm = torch.zeros(b, k, k, device="cuda")
+    ops.shampoo_stats(Gc, None, cols, rows * cols, L, Rm, b, k, k, 0.95, 0.05)
+    gf = G.float()[:, :k, :k]
+    assert rel(L, 0.05 * gf @ gf.transpose(1, 2)) < 1e-5 and rel(Rm, 0.05 * gf.transpose(1, 2) @ gf) < 1e-5
+    PL, PR = torch.empty_like(L), torch.empty_like(Rm)
+    hl = [torch.empty(b, k, k, device="cuda", dtype=torch.bfloat16) for _ in range(4)]
+    ops.shampoo_root(L, PL, hl[0], hl[1], k, 0.75, 1e-6, 6)
+    ops.shampoo_root(Rm, PR, hl[2], hl[3], k, 0.75, 1e-6, 6)
+    for i in range(b):
+        assert rel(PL[i], R.matrix_inverse_pth_root(L[i].cpu(), 0.75)) < SH_TOL, i
+        assert rel(PR[i], R.matrix_inverse_pth_root(Rm[i].cpu(), 0.75)) < SH_TOL, i
+    m = torch.randn(b, rows, cols) * 0.01
+    mh, ml = _split(m.cuda())
+    out = m.cuda().clone().contiguous()
+    ops.shampoo_precond(hl[0], hl[1], hl[2], hl[3], mh, ml, cols, rows * cols, out, cols, rows * cols, b, k, k, -0.01)
+    ref = m.clone()
+    for i in range(b):
+        ref[i, :k, :k] = -0.01 * (PL[i].cpu().double() @ m[i, :k, :k].double() @ PR[i].cpu().double()).float()
+    assert rel(out, ref) < 2e-4
+    assert torch.equal(out[:, k:], m.cuda()[:, k:])          # rows beyond the preconditioned block pass through

@@ -261,3 +261,24 @@ def test_markov_synthetic_stream_matches_oracle_generator():
         assert torch.equal(a, R.synthetic_batch_markov(step, rank, 3, 96, 256))
     u = SyntheticData(256, 3, 96, 0).generate_batch(5)
     assert torch.equal(u, R.synthetic_batch(5, 0, 3, 96, 256))
+
+
+def test_bench_workload_tables_match_baseline():
+    """bench.py derives every workload from configs/*.yaml; its algorithmic-work tables must reproduce BASELINE.md
+    section 4 (Newton-Schulz flops per update, attention flops and bytes per micro-batch x accumulation)."""
+    import bench
+    want_ns = {"c2": 4.129, "c3": 6.566, "c4": 5.413, "c5": 43.30}
+    want_attn = {"c1": (0.034, 0.069, 0.138), "c2": (0.825, 1.221, 2.441), "c4": (17.59, 17.31, 34.63),
+                 "c5": (17.59, 17.25, 34.49)}
+    for tag in bench.CONFIG_FILES:
+        c = bench.dims_of(bench.load_config(tag, False))
+        if tag in want_ns:
+            assert abs(bench.ns_flops_per_step(c) / 1e12 - want_ns[tag]) < 5e-3 * want_ns[tag], tag
+        if tag in want_attn:
+            f, bf, bb = want_attn[tag]
+            assert abs(bench.attn_flops_fwd_per_step(c) / 1e12 - f) < 2e-2 * f + 1e-3, tag
+            got_f, got_b = bench.attn_bytes_per_step(c)
+            assert abs(got_f / 1e9 - bf) < 1e-2 * bf + 1e-3 and abs(got_b / 1e9 - bb) < 1e-2 * bb + 1e-3, tag
+    c3 = bench.dims_of(bench.load_config("c3", False))
+    assert c3["accum"] == 8 and abs(bench.attn_flops_fwd_per_step(c3) / 1e12 - 8 * 4.398) < 0.05   # per update
+    assert "Muon" in bench.workload_name("c2", bench.dims_of(bench.load_config("c2", False)))
