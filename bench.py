@@ -360,9 +360,11 @@ def run_workload(tag: str, K: int, W: int, with_e2e: bool = True, with_dp_check:
     launches0 = lib().b200_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    h0 = time.perf_counter()
     for u in range(W, W + K):
         loss = update_resident(u)
-    e1.record()
+    host_issue_ms = 1e3 * (time.perf_counter() - h0) / K     # CPU time to ISSUE a step (no sync inside): << ms_per_step
+    e1.record()                                              # means the device, not the host, sets the pace
     sync_all()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     launches = int(lib().b200_launch_count() - launches0)
@@ -477,7 +479,7 @@ def run_workload(tag: str, K: int, W: int, with_e2e: bool = True, with_dp_check:
     if world > 1:
         dp.barrier()
     out = {"tag": tag, "c": c, "rank": rank, "world": world, "value": value, "ms_per_step": ms_per_step,
-           "tokens_per_step": tokens_per_step, "launches": launches, "kt": kt, "clocks": clocks, "final_loss": final_loss,
+           "tokens_per_step": tokens_per_step, "launches": launches, "host_issue_ms": host_issue_ms, "kt": kt, "clocks": clocks, "final_loss": final_loss,
            "e2e": e2e, "dp_check": dp_check, "K": K, "W": W}
     # flops of the matrices THIS rank orthogonalised (all of them unless the owner-computes mode is on)
     optm = getattr(tr.optimizer, "matrix_optimizer", tr.optimizer)
@@ -488,6 +490,27 @@ def run_workload(tag: str, K: int, W: int, with_e2e: bool = True, with_dp_check:
             owned = sum(hi_ - lo_ for lo_, hi_ in optm.owned_ranges_of(gi, world if sharded else 1, rank))
             fl += owned * ns_flops((g.rows, g.cols))
         out.update(ns_flops_rank=fl, ns_sharded=sharded, ns_exchange=getattr(optm, "exchange_mode", None))
+        if sharded:
+            # every rank's Newton-Schulz bracket and flops: the slowest rank sets the step (the others wait at the
+            # exchange barrier), so the JSON line can name the limiter
+            mine = torch.tensor([kt.get("newton_schulz", (0.0, 0))[0] / K, fl / 1e12], device=dev, dtype=torch.float64)
+            allr = [torch.zeros_like(mine) for _ in range(world)]
+            torch.distributed.all_gather(allr, mine)
+            ms_r, tf_r = [float(t[0]) for t in allr], [float(t[1]) for t in allr]
+            slow = max(range(world), key=lambda i: ms_r[i])
+            share = sum(tf_r) / world
+            why = ("flop-balanced ownership; the spread is the last GEMM's peer stores sharing NVLink with the all-gather "
+                   "of every rank's updates (2 bytes x all matrix parameters into each rank per step)")
+            if tf_r[slow] > 1.15 * share:
+                why = (f"this rank's largest matrix is one indivisible chain above the per-rank share of {share:.2f} TFLOP "
+                       "(C2 at 8 ranks: the 32003 x 1024 embedding, 0.68 TFLOP, 0.65 ms when timed alone on an idle GPU: "
+                       "tools/ns_single_probe.py), and its last GEMM's peer stores share NVLink with the all-gather of "
+                       "every rank's updates (2 bytes x all matrix parameters into each rank per step)")
+            out["ns_ranks"] = {
+                "ns_ms_per_rank": [round(x, 3) for x in ms_r], "ns_tflop_per_rank": [round(x, 3) for x in tf_r],
+                "slowest_rank": slow,
+                "limiter": (f"rank {slow}: {ms_r[slow]:.2f} ms for {tf_r[slow]:.2f} TFLOP (mean of the others "
+                            f"{(sum(ms_r) - ms_r[slow]) / max(1, world - 1):.2f} ms); " + why)}
     del tr
     torch.cuda.empty_cache()
     return out
@@ -531,6 +554,8 @@ def summarize(r: dict, peaks: dict) -> dict:
                     "frac_of_burst": tf / peak_burst, "algorithmic_flops_per_step": r["ns_flops_rank"],
                     "algorithmic_flops_all_ranks": ns_flops_per_step(c), "ns_sharded_over_ranks": r["ns_sharded"],
                     "ns_exchange": r["ns_exchange"], "ms_per_step": ns_step, "share_of_step": ns_step / r["ms_per_step"]}
+        if r.get("ns_ranks"):
+            roofline.update(r["ns_ranks"])
     elif "attn_bwd" in kernels:
         kb = kernels["attn_bwd"]
         roofline = {"kernel": "attn_bwd (fused causal/GQA attention backward, tcgen05; 2.5 x 4BHS^2D flops, full count)",
@@ -581,7 +606,7 @@ def main() -> None:
         "config": {"workload": workload_name(tag, c), "global_batch": c["batch"] * world, "seq_len": c["seq"],
                    "micro_batches_per_step": c["accum"], "parallelism": f"dp{world}",
                    "l2": "working set (params+grads+activations, GBs) >> 126 MB L2"},
-        "e2e": r["e2e"], "gpu_launches": r["launches"], "clocks": r["clocks"], "roofline": s["roofline"],
+        "e2e": r["e2e"], "gpu_launches": r["launches"], "host_issue_ms_per_step": r["host_issue_ms"], "clocks": r["clocks"], "roofline": s["roofline"],
         "kernels": s["kernels"], "final_loss": r["final_loss"],
     }
     if r["dp_check"] is not None:
