@@ -32,6 +32,8 @@ int b200_version(void);                 /* ABI version (monotonic integer) */
 const char* b200_last_error(void);      /* thread-local message of the last failing call */
 int b200_device_ok(void);               /* 1 if the current device is compute capability 10.x */
 unsigned long long b200_launch_count(void); /* kernels launched by this library so far (process-wide) */
+/* TMA descriptors are cached per (address, shape, strides, box): calls answered from the cache / encoded by the driver */
+void b200_tensor_map_cache_stats(unsigned long long* hits, unsigned long long* misses);
 
 /* ---- dense contraction engine (tcgen05 + TMA) ----------------------------------------------
  * D[b] = alpha*alpha_vec[b] * op(A[b]) op(B[b]) + beta*beta_vec[b] * C[b],  b in [0,batch)
@@ -185,8 +187,23 @@ int b200_rmsnorm_fwd(const void* x, const void* w, void* y, float* rstd, int row
                      float eps, int is_bf16, void* stream);
 size_t b200_rmsnorm_bwd_workspace_bytes(int rows, int H);   /* per-CTA dW partials */
 int b200_rmsnorm_bwd(const void* dy, const void* x, const void* w, const float* rstd, void* dx,
-                     float* dw_f32, int rows, int H, int is_bf16, void* workspace,
+                     float* dw_f32 /* NULL: deferred, see below */, int rows, int H, int is_bf16, void* workspace,
                      size_t workspace_bytes, void* stream);
+/* Deferred weight gradient: (add_)rmsnorm_bwd called with dw_f32 == NULL leaves its per-CTA partial sums
+ * [b200_rmsnorm_bwd_partial_rows(rows, H)][H] (fp32) in the workspace; b200_rmsnorm_dw_reduce then folds any number of
+ * such workspaces (one job per norm, all of width H) in one launch per 32 jobs, writing or accumulating into each
+ * weight's gradient in its storage type -- the backward of an L-layer model reduces its 2L+1 norm weights once, after
+ * the last layer, instead of with four small launches per norm. */
+typedef struct b200_dw_job {
+  const float* partials; /* workspace of the matching (add_)rmsnorm_bwd call */
+  void* dw;              /* [H] bf16 or fp32 */
+  int n_partials;        /* b200_rmsnorm_bwd_partial_rows(rows, H) of that call */
+  int dw_is_bf16;
+  int accumulate;        /* 1: dw += sum (autograd semantics), 0: dw = sum */
+  int reserved;
+} b200_dw_job;
+int b200_rmsnorm_bwd_partial_rows(int rows, int H);
+int b200_rmsnorm_dw_reduce(const b200_dw_job* jobs, int n_jobs, int H, void* stream);
 /* Residual add fused with the norm that follows it (arch/llama.py:316-319: h = x + sublayer(...), then
  * the next norm reads h):  sum_out = x + delta (rounded to the storage type), y = rmsnorm(sum_out) * w.
  * Backward: dx = dres + rmsnorm_bwd(dy) where dres (nullable) is the gradient that reached sum_out

@@ -21,6 +21,7 @@ SIGNATURES = {
     "b200_last_error": (C.c_char_p, []),
     "b200_device_ok": (_i, []),
     "b200_launch_count": (C.c_ulonglong, []),
+    "b200_tensor_map_cache_stats": (None, [C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]),
     "b200_gemm_bf16": (_i, [_i, _i, _i, _i, _i, _i, _vp, _ll, _ll, _vp, _ll, _ll, _vp, _ll, _ll,
                             _vp, _ll, _ll, _i, _f, _f, _vp, _vp, _i, _vp]),
     "b200_newton_schulz_workspace_bytes": (_sz, [_i, _i, _i, _i]),
@@ -49,6 +50,7 @@ SIGNATURES = {
     "b200_rmsnorm_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _f, _i, _vp]),
     "b200_rmsnorm_bwd_workspace_bytes": (_sz, [_i, _i]),
     "b200_rmsnorm_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _sz, _vp]),
+    "b200_rmsnorm_bwd_partial_rows": (_i, [_i, _i]),
     "b200_add_rmsnorm_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _i, _vp]),
     "b200_add_rmsnorm_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _sz, _vp]),
     "b200_rope": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
@@ -75,6 +77,13 @@ class NsGroup(C.Structure):
                 ("inv_norm_sq", _vp), ("peer_out", C.POINTER(_vp)), ("n_peers", _i)]
 
 
+class DwJob(C.Structure):
+    """b200_dw_job (include/b200_hotpath.h)"""
+    _fields_ = [("partials", _vp), ("dw", _vp), ("n_partials", _i), ("dw_is_bf16", _i), ("accumulate", _i),
+                ("reserved", _i)]
+
+
+SIGNATURES["b200_rmsnorm_dw_reduce"] = (_i, [C.POINTER(DwJob), _i, _i, _vp])
 SIGNATURES["b200_newton_schulz_multi_workspace_bytes"] = (_sz, [C.POINTER(NsGroup), _i, _i])
 SIGNATURES["b200_newton_schulz_multi"] = (_i, [C.POINTER(NsGroup), _i, _i, _f, _f, _f, _vp, _sz, _vp])
 

@@ -75,6 +75,8 @@ size_t rmsnorm_bwd_workspace_bytes(int rows, int H);
 int rmsnorm_bwd(const void* dy, const void* x, const void* w, const float* rstd, void* dx,
                 float* dw, int rows, int H, int is_bf16, void* ws, size_t ws_bytes,
                 cudaStream_t stream);
+int rmsnorm_bwd_partial_rows(int rows, int H);
+int rmsnorm_dw_reduce(const DwJob* jobs, int n_jobs, int H, cudaStream_t stream);
 int add_rmsnorm_fwd(const void* x, const void* delta, const void* w, void* sum_out, void* y, float* rstd,
                     int rows, int H, float eps, int is_bf16, cudaStream_t stream);
 int add_rmsnorm_bwd(const void* dy, const void* dres, const void* x, const void* w, const float* rstd,
@@ -104,6 +106,10 @@ int b200_version(void) { return 2; }
 const char* b200_last_error(void) { return b200::last_error(); }
 
 unsigned long long b200_launch_count(void) { return b200::launch_count(); }
+void b200_tensor_map_cache_stats(unsigned long long* hits, unsigned long long* misses) {
+  if (hits) *hits = b200::tensor_map_cache_hits();
+  if (misses) *misses = b200::tensor_map_cache_misses();
+}
 
 int b200_device_ok(void) {
   int dev = 0, major = 0;
@@ -248,6 +254,11 @@ int b200_rmsnorm_bwd(const void* dy, const void* x, const void* w, const float* 
                      size_t workspace_bytes, void* stream) {
   return b200::rmsnorm_bwd(dy, x, w, rstd, dx, dw_f32, rows, H, is_bf16, workspace, workspace_bytes,
                            S_(stream));
+}
+int b200_rmsnorm_bwd_partial_rows(int rows, int H) { return b200::rmsnorm_bwd_partial_rows(rows, H); }
+static_assert(sizeof(b200_dw_job) == sizeof(b200::DwJob), "b200_dw_job layout");
+int b200_rmsnorm_dw_reduce(const b200_dw_job* jobs, int n_jobs, int H, void* stream) {
+  return b200::rmsnorm_dw_reduce(reinterpret_cast<const b200::DwJob*>(jobs), n_jobs, H, S_(stream));
 }
 int b200_add_rmsnorm_fwd(const void* x, const void* delta, const void* w, void* sum_out, void* y,
                          float* rstd, int rows, int H, float eps, int is_bf16, void* stream) {

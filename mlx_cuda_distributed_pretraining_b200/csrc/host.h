@@ -34,7 +34,18 @@ const char* last_error();
 
 // every kernel launch of the library is counted (bench.py reports it as gpu_launches)
 void count_launch();
+// one deferred RMSNorm weight-gradient reduction (mirrors b200_dw_job of include/b200_hotpath.h)
+struct DwJob {
+  const float* partials;  // [n_partials][H] fp32, left in the workspace by (add_)rmsnorm_bwd with dw == nullptr
+  void* dw;               // [H] bf16 or fp32
+  int n_partials;
+  int dw_is_bf16;
+  int accumulate;         // 1: dw += sum, 0: dw = sum
+  int reserved;
+};
 unsigned long long launch_count();
+unsigned long long tensor_map_cache_hits();     // make_tensor_map calls answered from the descriptor cache
+unsigned long long tensor_map_cache_misses();   // ... that went to cuTensorMapEncodeTiled
 
 #define B200_CHECK_LAUNCH()                  \
   do {                                       \

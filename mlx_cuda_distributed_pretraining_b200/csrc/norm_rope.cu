@@ -389,6 +389,48 @@ rmsnorm_dw_reduce_kernel(const float* __restrict__ dw_part, float* __restrict__ 
   }
 }
 
+// The same column sum for up to 32 norms in ONE launch (blockIdx.y = job), accumulating straight into the weight's
+// gradient in its storage type: a Llama backward has 2 norms per layer, and each used to cost four launches (partials,
+// this reduction, a dtype copy and autograd's accumulate) -- ~100 sub-10-us kernels per C2 step, mostly launch latency.
+struct DwJobs {
+  b200::DwJob j[32];
+};
+__global__ void __launch_bounds__(1024) rmsnorm_dw_reduce_batched_kernel(const __grid_constant__ DwJobs jobs, int H) {
+  __shared__ float part[32][33];
+  const b200::DwJob& job = jobs.j[blockIdx.y];
+  const float* __restrict__ dw_part = job.partials;
+  const int nblocks = job.n_partials;
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  if (c < H) {
+    int b = ry;
+    for (; b + 96 < nblocks; b += 128) {
+      s0 += dw_part[(long long)b * H + c];
+      s1 += dw_part[(long long)(b + 32) * H + c];
+      s2 += dw_part[(long long)(b + 64) * H + c];
+      s3 += dw_part[(long long)(b + 96) * H + c];
+    }
+    for (; b < nblocks; b += 32) s0 += dw_part[(long long)b * H + c];
+  }
+  part[ry][cx] = (s0 + s1) + (s2 + s3);
+  __syncthreads();
+  if (ry == 0 && c < H) {
+    float t = 0.f;
+#pragma unroll
+    for (int r = 0; r < 32; ++r) t += part[r][cx];
+    if (job.dw_is_bf16) {
+      __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(job.dw);
+      if (job.accumulate) t += __bfloat162float(d[c]);
+      d[c] = __float2bfloat16(t);
+    } else {
+      float* d = reinterpret_cast<float*>(job.dw);
+      if (job.accumulate) t += d[c];
+      d[c] = t;
+    }
+  }
+}
+
 // x: [B, S, NH, D]; cos/sin: [S, D/2] fp32. out[2i] = x[2i]*c - x[2i+1]*s ; out[2i+1] = x[2i]*s +
 // x[2i+1]*c. The backward pass is the same rotation with sign = -1.
 template <typename T>
@@ -486,6 +528,7 @@ int rmsnorm_bwd_t(const T* dy, const T* dres, const T* x, const T* w, const floa
     else rmsnorm_bwd_kernel<T, RN_MAX_VEC><<<grid, RN_THREADS, 0, stream>>>(dy, dres, x, w, rstd, dx, dw_part, rows, H);
   }
   B200_CHECK_LAUNCH();
+  if (dw == nullptr) return B200_OK;   // partials stay in the workspace for rmsnorm_dw_reduce (deferred, batched)
   rmsnorm_dw_reduce_kernel<<<(H + 31) / 32, 1024, 0, stream>>>(dw_part, dw, grid, H);
   B200_CHECK_LAUNCH();
   return B200_OK;
@@ -519,6 +562,23 @@ int rmsnorm_fwd(const void* x, const void* w, void* y, float* rstd, int rows, in
 
 size_t rmsnorm_bwd_workspace_bytes(int rows, int H) {
   return (size_t)rmsnorm_bwd_grid(rows, H) * H * sizeof(float);
+}
+
+int rmsnorm_bwd_partial_rows(int rows, int H) { return rmsnorm_bwd_grid(rows, H); }
+
+int rmsnorm_dw_reduce(const DwJob* jobs, int n_jobs, int H, cudaStream_t stream) {
+  B200_CHECK_ARG(n_jobs >= 0 && H > 0 && (jobs != nullptr || n_jobs == 0), "rmsnorm_dw_reduce: bad arguments");
+  for (int i = 0; i < n_jobs; ++i)
+    B200_CHECK_ARG(jobs[i].partials != nullptr && jobs[i].dw != nullptr && jobs[i].n_partials > 0,
+                   "rmsnorm_dw_reduce: job %d has a null pointer or no partial rows", i);
+  for (int i = 0; i < n_jobs; i += 32) {
+    DwJobs a;
+    const int n = n_jobs - i < 32 ? n_jobs - i : 32;
+    for (int k = 0; k < n; ++k) a.j[k] = jobs[i + k];
+    rmsnorm_dw_reduce_batched_kernel<<<dim3((H + 31) / 32, n), 1024, 0, stream>>>(a, H);
+    B200_CHECK_LAUNCH();
+  }
+  return B200_OK;
 }
 
 int add_rmsnorm_bwd(const void* dy, const void* dres, const void* x, const void* w, const float* rstd,

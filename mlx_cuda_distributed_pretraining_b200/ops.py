@@ -7,6 +7,7 @@ there is no eager fallback.
 from __future__ import annotations
 
 import math
+import os
 from typing import Optional, Sequence, Tuple
 
 import torch
@@ -295,6 +296,45 @@ def split_bf16(src: torch.Tensor, rows: int, cols: int, hi: torch.Tensor,
 # ------------------------------------------------------------------------------------------------
 # RMSNorm / RoPE / attention as autograd functions
 # ------------------------------------------------------------------------------------------------
+# Deferred RMSNorm weight gradients: a norm's backward leaves its per-CTA partial sums in a workspace; ONE batched
+# launch at the end of the backward pass (an autograd-engine callback) folds all of them into the weights' .grad
+# buffers in place.  Used when the weight is a leaf with a preallocated contiguous .grad (the flat ParamStore's
+# case); any other weight takes the immediate path and gets its gradient from autograd as usual.
+_PENDING_DW: list = []
+_DW_DEFER = os.environ.get("B200_DEFER_DW", "1") != "0"
+
+
+def _dw_target(w: torch.Tensor) -> Optional[torch.Tensor]:
+    g = w.grad if (_DW_DEFER and w.is_leaf and w.requires_grad) else None
+    if g is None or not g.is_contiguous() or g.dtype not in (torch.bfloat16, torch.float32) or g.shape != w.shape:
+        return None
+    return g
+
+
+def flush_deferred_dw() -> None:
+    """Runs the pending weight-gradient reductions now (normally called by the autograd engine at the end of the
+    backward pass that queued them)."""
+    if not _PENDING_DW:
+        return
+    from ._lib import DwJob
+    jobs, _PENDING_DW[:] = list(_PENDING_DW), []
+    by_h = {}
+    for ws, grad, nparts in jobs:
+        by_h.setdefault(grad.numel(), []).append((ws, grad, nparts))
+    for H, group in by_h.items():
+        arr = (DwJob * len(group))()
+        for i, (ws, grad, nparts) in enumerate(group):
+            arr[i].partials, arr[i].dw, arr[i].n_partials = ws.data_ptr(), grad.data_ptr(), nparts
+            arr[i].dw_is_bf16, arr[i].accumulate = int(grad.dtype == torch.bfloat16), 1
+        check(lib().b200_rmsnorm_dw_reduce(arr, len(group), H, _stream()), "b200_rmsnorm_dw_reduce")
+
+
+def _defer_dw(ws: torch.Tensor, grad: torch.Tensor, nparts: int) -> None:
+    if not _PENDING_DW:
+        torch.autograd.Variable._execution_engine.queue_callback(flush_deferred_dw)
+    _PENDING_DW.append((ws, grad, nparts))
+
+
 class _RMSNormFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w, eps):
@@ -308,6 +348,7 @@ class _RMSNormFn(torch.autograd.Function):
               "b200_rmsnorm_fwd")
         ctx.save_for_backward(xs, wc, rstd)
         ctx.w_dtype = w.dtype
+        ctx.weight = w
         return y
 
     @staticmethod
@@ -316,11 +357,15 @@ class _RMSNormFn(torch.autograd.Function):
         dy = dy.contiguous()
         rows, H = xs.numel() // xs.shape[-1], xs.shape[-1]
         dx = torch.empty_like(xs)
-        dw = torch.empty(H, device=xs.device, dtype=torch.float32)
+        target = _dw_target(ctx.weight)
+        dw = None if target is not None else torch.empty(H, device=xs.device, dtype=torch.float32)
         ws = torch.empty(int(lib().b200_rmsnorm_bwd_workspace_bytes(rows, H)), device=xs.device, dtype=torch.uint8)
         check(lib().b200_rmsnorm_bwd(dy.data_ptr(), xs.data_ptr(), wc.data_ptr(), rstd.data_ptr(),
-                                     dx.data_ptr(), dw.data_ptr(), rows, H, _is_bf16(xs, "x"),
+                                     dx.data_ptr(), _ptr(dw), rows, H, _is_bf16(xs, "x"),
                                      ws.data_ptr(), ws.numel(), _stream()), "b200_rmsnorm_bwd")
+        if target is not None:
+            _defer_dw(ws, target, int(lib().b200_rmsnorm_bwd_partial_rows(rows, H)))
+            return dx, None, None
         return dx, dw.to(ctx.w_dtype), None
 
 
@@ -345,6 +390,7 @@ class _AddRMSNormFn(torch.autograd.Function):
               "b200_add_rmsnorm_fwd")
         ctx.save_for_backward(s, wc, rstd)
         ctx.w_dtype = w.dtype
+        ctx.weight = w
         ctx.set_materialize_grads(False)
         return s, y
 
@@ -356,13 +402,17 @@ class _AddRMSNormFn(torch.autograd.Function):
         dy = dy.contiguous()
         rows, H = s.numel() // s.shape[-1], s.shape[-1]
         dx = torch.empty_like(s)
-        dw = torch.empty(H, device=s.device, dtype=torch.float32)
+        target = _dw_target(ctx.weight)
+        dw = None if target is not None else torch.empty(H, device=s.device, dtype=torch.float32)
         ws = torch.empty(int(lib().b200_rmsnorm_bwd_workspace_bytes(rows, H)), device=s.device, dtype=torch.uint8)
         dres = ds.contiguous() if ds is not None else None
         check(lib().b200_add_rmsnorm_bwd(dy.data_ptr(), dres.data_ptr() if dres is not None else None,
                                          s.data_ptr(), wc.data_ptr(), rstd.data_ptr(), dx.data_ptr(),
-                                         dw.data_ptr(), rows, H, _is_bf16(s, "x"), ws.data_ptr(), ws.numel(),
+                                         _ptr(dw), rows, H, _is_bf16(s, "x"), ws.data_ptr(), ws.numel(),
                                          _stream()), "b200_add_rmsnorm_bwd")
+        if target is not None:
+            _defer_dw(ws, target, int(lib().b200_rmsnorm_bwd_partial_rows(rows, H)))
+            return dx, dx, None, None
         return dx, dx, dw.to(ctx.w_dtype), None
 
 

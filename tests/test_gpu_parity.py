@@ -65,6 +65,36 @@ def test_gemm_epilogue(ops):
     assert rel(acc, prod + c32) < 2e-6
 
 
+def test_tensor_map_cache_answers_repeated_launches(ops):
+    """The host encodes a TMA descriptor once per (address, shape, strides, box): a repeated launch on the same buffers
+    must be served from the cache and compute the same result; a different shape on the same storage must not."""
+    import ctypes
+    from mlx_cuda_distributed_pretraining_b200._lib import lib
+
+    def stats():
+        h, m = ctypes.c_ulonglong(0), ctypes.c_ulonglong(0)
+        lib().b200_tensor_map_cache_stats(ctypes.byref(h), ctypes.byref(m))
+        return h.value, m.value
+
+    torch.manual_seed(3)
+    a = torch.randn(1, 512, 384, device="cuda").to(torch.bfloat16)
+    b = torch.randn(1, 256, 384, device="cuda").to(torch.bfloat16)
+    out = torch.empty(1, 512, 256, device="cuda", dtype=torch.float32)
+    ops.gemm(a, b, out=out)
+    first = out.clone()
+    h0, m0 = stats()
+    ops.gemm(a, b, out=out)
+    h1, m1 = stats()
+    assert m1 == m0 and h1 >= h0 + 2, (h0, m0, h1, m1)          # both operand maps came from the cache
+    assert torch.equal(out, first)
+    # same storage viewed with another shape: new descriptors, right answer
+    a2, b2 = a.view(1, 256, 768), b.view(1, 128, 768)
+    out2 = ops.gemm(a2, b2, out_dtype=torch.float32)
+    h2, m2 = stats()
+    assert m2 > m1
+    assert rel(out2, torch.bmm(a2.float(), b2.float().transpose(1, 2))) < 2e-6
+
+
 def test_gemm_rejects_bad_arguments(ops):
     from mlx_cuda_distributed_pretraining_b200._lib import B200Error
     a = torch.zeros(16, 12, device="cuda", dtype=torch.bfloat16)   # K = 12: 24-byte rows, not TMA-able
@@ -327,6 +357,45 @@ def test_multi_linear_fused_kv_backward(ops):
 def test_rmsnorm_golden(ops, golden):
     x, w = torch.from_numpy(golden["rms_x"]).cuda(), torch.from_numpy(golden["rms_w"]).cuda()
     assert rel(ops.rmsnorm(x, w, 1e-5), golden["rms_y"]) < 2e-6
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_rmsnorm_deferred_weight_gradients(ops, dtype):
+    """Leaf weights with a preallocated .grad (the flat store's case) get their gradient from ONE batched reduction
+    at the end of the backward pass, accumulated in place; it must equal the immediate path's autograd result."""
+    torch.manual_seed(11)
+    rows, H, L = 777, 1024, 5
+    x0 = torch.randn(rows, H, device="cuda").to(dtype)
+    deltas = [torch.randn(rows, H, device="cuda").to(dtype) * 0.3 for _ in range(L)]
+
+    def run(defer: bool, passes: int):
+        ops._DW_DEFER = defer
+        try:
+            ws = [torch.nn.Parameter((1 + 0.1 * torch.randn(H, generator=torch.Generator().manual_seed(i))).cuda().to(dtype))
+                  for i in range(L + 1)]
+            for w in ws:
+                w.grad = torch.zeros_like(w) if defer else None
+            x = x0.clone().requires_grad_(True)
+            for _ in range(passes):
+                h = ops.rmsnorm(x, ws[0])
+                for i in range(L):
+                    h, y = ops.add_rmsnorm(h, deltas[i], ws[i + 1])
+                    h = h + 0.5 * y
+                (h.float() ** 2).mean().backward()
+            assert not ops._PENDING_DW
+            return [w.grad.float().clone() for w in ws], x.grad.float().clone()
+        finally:
+            ops._DW_DEFER = True
+
+    tol = 2e-2 if dtype == torch.bfloat16 else 1e-5     # bf16: one rounding (in-place accumulate) vs two (copy + add)
+    g_def, dx_def = run(True, 1)
+    g_imm, dx_imm = run(False, 1)
+    assert torch.equal(dx_def, dx_imm)
+    for a, b in zip(g_def, g_imm):
+        assert rel(a, b) < tol
+    g2, _ = run(True, 2)                                 # a second backward accumulates
+    for a, b in zip(g2, g_def):
+        assert rel(a, 2 * b) < tol
 
 
 @pytest.mark.parametrize("D", [16, 64, 128])
