@@ -140,6 +140,9 @@ class ClockSampler:
     def stop(self) -> dict:
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        t_end = time.perf_counter() + 0.5
+        while not self.rows and time.perf_counter() < t_end:   # timed region shorter than one 100 ms sample (C1):
+            time.sleep(0.02)                                   # take the first sample that arrives right after it
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)

@@ -357,16 +357,16 @@ class _RMSNormFn(torch.autograd.Function):
         dy = dy.contiguous()
         rows, H = xs.numel() // xs.shape[-1], xs.shape[-1]
         dx = torch.empty_like(xs)
-        target = _dw_target(ctx.weight)
-        dw = None if target is not None else torch.empty(H, device=xs.device, dtype=torch.float32)
+        need_w = ctx.needs_input_grad[1]
+        target = _dw_target(ctx.weight) if need_w else None
+        dw = None if (target is not None or not need_w) else torch.empty(H, device=xs.device, dtype=torch.float32)
         ws = torch.empty(int(lib().b200_rmsnorm_bwd_workspace_bytes(rows, H)), device=xs.device, dtype=torch.uint8)
         check(lib().b200_rmsnorm_bwd(dy.data_ptr(), xs.data_ptr(), wc.data_ptr(), rstd.data_ptr(),
                                      dx.data_ptr(), _ptr(dw), rows, H, _is_bf16(xs, "x"),
                                      ws.data_ptr(), ws.numel(), _stream()), "b200_rmsnorm_bwd")
         if target is not None:
             _defer_dw(ws, target, int(lib().b200_rmsnorm_bwd_partial_rows(rows, H)))
-            return dx, None, None
-        return dx, dw.to(ctx.w_dtype), None
+        return dx, (dw.to(ctx.w_dtype) if dw is not None else None), None
 
 
 def rmsnorm(x: torch.Tensor, w: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
@@ -402,8 +402,9 @@ class _AddRMSNormFn(torch.autograd.Function):
         dy = dy.contiguous()
         rows, H = s.numel() // s.shape[-1], s.shape[-1]
         dx = torch.empty_like(s)
-        target = _dw_target(ctx.weight)
-        dw = None if target is not None else torch.empty(H, device=s.device, dtype=torch.float32)
+        need_w = ctx.needs_input_grad[2]
+        target = _dw_target(ctx.weight) if need_w else None
+        dw = None if (target is not None or not need_w) else torch.empty(H, device=s.device, dtype=torch.float32)
         ws = torch.empty(int(lib().b200_rmsnorm_bwd_workspace_bytes(rows, H)), device=s.device, dtype=torch.uint8)
         dres = ds.contiguous() if ds is not None else None
         check(lib().b200_add_rmsnorm_bwd(dy.data_ptr(), dres.data_ptr() if dres is not None else None,
@@ -412,8 +413,7 @@ class _AddRMSNormFn(torch.autograd.Function):
                                          _stream()), "b200_add_rmsnorm_bwd")
         if target is not None:
             _defer_dw(ws, target, int(lib().b200_rmsnorm_bwd_partial_rows(rows, H)))
-            return dx, dx, None, None
-        return dx, dx, dw.to(ctx.w_dtype), None
+        return dx, dx, (dw.to(ctx.w_dtype) if dw is not None else None), None
 
 
 def add_rmsnorm(x: torch.Tensor, delta: torch.Tensor, w: torch.Tensor, eps: float = 1e-5):

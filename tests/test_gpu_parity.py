@@ -393,6 +393,11 @@ def test_rmsnorm_deferred_weight_gradients(ops, dtype):
     assert torch.equal(dx_def, dx_imm)
     for a, b in zip(g_def, g_imm):
         assert rel(a, b) < tol
+    # a frozen weight (requires_grad False) takes no gradient at all
+    w = torch.ones(H, device="cuda", dtype=dtype)
+    x = x0.clone().requires_grad_(True)
+    ops.rmsnorm(x, w).float().sum().backward()
+    assert torch.isfinite(x.grad).all() and w.grad is None and not ops._PENDING_DW
     g2, _ = run(True, 2)                                 # a second backward accumulates
     for a, b in zip(g2, g_def):
         assert rel(a, 2 * b) < tol
