@@ -6,7 +6,6 @@ there is no eager fallback.
 """
 from __future__ import annotations
 
-import math
 import os
 from typing import Optional, Sequence, Tuple
 
@@ -210,7 +209,6 @@ def zeropower_groups(gs: Sequence[torch.Tensor], steps: int = 5, eps: float = NS
     """Newton-Schulz of several [batch, rows, cols] groups (different shapes) through the whole-model chain:
     every stage of the iteration is ONE grouped launch over all groups (b200_newton_schulz_multi).
     Returns a list of bf16 tensors shaped like the inputs."""
-    import ctypes
     from ._lib import NsGroup
     require_device()
     if not 1 <= len(gs) <= 6:
@@ -931,10 +929,9 @@ def mlp(x: torch.Tensor, wg: torch.Tensor, wu: torch.Tensor, wd: torch.Tensor) -
     return linear(glu(g, u), wd)
 
 
-import os as _os
 # B200_MLP_FUSED=0 restores the library GEMMs + elementwise GLU kernels (A/B switch for measurements; the first
 # version of the fused epilogues, with row-per-lane 16-byte stores, LOST to that pair -- see DESIGN.md section 4.6)
-_MLP_FUSED = _os.environ.get("B200_MLP_FUSED", "1") != "0"
+_MLP_FUSED = os.environ.get("B200_MLP_FUSED", "1") != "0"
 
 
 def glu(gate: torch.Tensor, up: torch.Tensor) -> torch.Tensor:
