@@ -614,6 +614,12 @@ def main() -> None:
     }
     if r["dp_check"] is not None:
         line["dp_check"] = r["dp_check"]
+        modes = r["dp_check"].get("exchange") or {}
+        ok = r["dp_check"]["replicas_bit_identical"] and all(m.get("replicas_bit_identical", True) for m in modes.values())
+        line["dp_check"]["passed"] = bool(ok)
+        if not ok:   # the number below is still printed, but a diverged replica set must not pass unnoticed
+            print("[bench] DATA-PARALLEL CHECK FAILED: replicas are not bit-identical: "
+                  + json.dumps(r["dp_check"]), file=sys.stderr, flush=True)
     if world == 1 and not args.no_cpu_baseline:
         try:
             threads = pick_cpu_threads(dims_of(load_config(tag, False)))

@@ -24,6 +24,7 @@ What is exercised (reference file:line):
   core/training.py:1195-1234   Trainer.compute_loss (masked token-mean cross-entropy) on the tiny Model
   core/training.py:764-856     OptimizationManager.create_scheduler (all three types) and the Shampoo branch of
                                create_optimizer (factory defaults -> ShampooParams)
+  core/training.py:621-668     EarlyStoppingMonitor: stop decisions / counter / best over validation-loss sequences
   core/training.py:52-166      Config.from_yaml on this repo's configs/c*.yaml -> tests/golden/ref_config_parse.json
   distributed/hybrid_distributed.py:303-354,430-452  HybridDeviceManager._aggregate_gradients /
                                distribute_batch (the data-parallel contract: unweighted mean, remainder
@@ -245,6 +246,28 @@ sh = ref_training.OptimizationManager(_tc({"type": "cosine", "min_lr_ratio": 0.1
 sh_opt = sh.create_optimizer(sh.create_scheduler())       # every Shampoo knob left to the factory's default
 for k, v in dataclasses.asdict(sh_opt.params).items():
     out[f"om_shampoo::{k}"] = np.array(v)
+
+# ---- EarlyStoppingMonitor (core/training.py:621-668): stop decisions over validation-loss sequences -------------
+es_rng = np.random.default_rng(77)            # its own generator: the arrays above do not move
+es_cases = [
+    ({"enabled": True, "patience": 3, "min_delta": 0.001}, np.concatenate([np.linspace(5.0, 3.0, 6), 3.0 + 0.0005 * np.arange(6)])),
+    ({"enabled": True, "patience": 2, "min_delta": 0.01}, 4.0 - 0.02 * np.arange(10) + 0.03 * es_rng.standard_normal(10)),
+    ({"enabled": True, "patience": 2, "min_delta": 0.0, "mode": "max", "metric": "val_loss"}, np.array([1.0, 1.5, 1.5, 1.4, 1.6, 1.6, 1.6])),
+    ({"enabled": False, "patience": 1}, np.array([3.0, 3.1, 3.2, 3.3])),
+    ({"enabled": True}, 3.0 + 0.1 * np.abs(es_rng.standard_normal(8))),       # all defaults
+]
+for i, (es_cfg, seq) in enumerate(es_cases):
+    mon = ref_training.EarlyStoppingMonitor(dict(es_cfg))
+    stops, counters, bests = [], [], []
+    for v in seq:
+        stops.append(int(bool(mon.update({"val_loss": float(v)}))))
+        counters.append(mon.counter)
+        bests.append(mon.best_value)
+    out[f"es{i}_seq"] = np.asarray(seq, dtype=np.float64)
+    out[f"es{i}_stop"] = np.asarray(stops)
+    out[f"es{i}_counter"] = np.asarray(counters)
+    out[f"es{i}_best"] = np.asarray(bests, dtype=np.float64)
+    out[f"es{i}_cfg"] = np.array(repr(sorted(es_cfg.items())))
 
 # ---- YAML schema: this repo's configs/*.yaml parsed by the REFERENCE's Config dataclasses (core/training.py:52-166)
 import json  # noqa: E402

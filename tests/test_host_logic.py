@@ -282,3 +282,23 @@ def test_bench_workload_tables_match_baseline():
     c3 = bench.dims_of(bench.load_config("c3", False))
     assert c3["accum"] == 8 and abs(bench.attn_flops_fwd_per_step(c3) / 1e12 - 8 * 4.398) < 0.05   # per update
     assert "Muon" in bench.workload_name("c2", bench.dims_of(bench.load_config("c2", False)))
+
+
+def test_early_stopping_matches_reference_decisions():
+    """EarlyStoppingMonitor vs the reference's own class run over five validation-loss sequences
+    (tests/golden/make_golden.py, core/training.py:621-668): same stop decision, counter and best value after
+    every update, for min / max mode, disabled monitors and all-default settings."""
+    import ast
+
+    import numpy as np
+    from mlx_cuda_distributed_pretraining_b200.core.training import EarlyStoppingMonitor
+    g = np.load(ROOT / "tests" / "golden" / "reference_vectors.npz")
+    n_cases = sum(1 for k in g.files if k.startswith("es") and k.endswith("_seq"))
+    assert n_cases == 5
+    for i in range(n_cases):
+        cfg = dict(ast.literal_eval(str(g[f"es{i}_cfg"])))
+        mon = EarlyStoppingMonitor(cfg)
+        for v, stop, counter, best in zip(g[f"es{i}_seq"], g[f"es{i}_stop"], g[f"es{i}_counter"], g[f"es{i}_best"]):
+            assert int(mon.update({"val_loss": float(v)})) == int(stop), (i, v)
+            assert mon.counter == int(counter) and mon.best_value == float(best), (i, v)
+    assert EarlyStoppingMonitor({"enabled": True}).update({"other_metric": 1.0}) is False   # metric absent: never stops
