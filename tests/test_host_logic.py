@@ -302,3 +302,26 @@ def test_early_stopping_matches_reference_decisions():
             assert int(mon.update({"val_loss": float(v)})) == int(stop), (i, v)
             assert mon.counter == int(counter) and mon.best_value == float(best), (i, v)
     assert EarlyStoppingMonitor({"enabled": True}).update({"other_metric": 1.0}) is False   # metric absent: never stops
+
+
+def test_header_is_plain_c_and_links_against_the_library(lib_built, tmp_path):
+    """include/b200_hotpath.h is the boundary a non-Python host binds: it must compile as C99 (no C++-isms, no torch
+    types) and a C program using it must link against the built library by its exported names alone."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "host.c"
+    src.write_text('#include <stddef.h>\n#include "b200_hotpath.h"\n'
+                   "int main(void) {\n"
+                   "  b200_dw_job j; b200_ns_group g; unsigned long long h = 0, m = 0;\n"
+                   "  (void)j; (void)g;\n"
+                   "  b200_tensor_map_cache_stats(&h, &m);\n"
+                   "  /* no device here: only calls that need none */\n"
+                   "  return (b200_version() >= 2 && b200_reduce_workspace_bytes(4) > 0 && h == 0 && m == 0) ? 0 : 1;\n"
+                   "}\n")
+    lib_dir = ROOT / "mlx_cuda_distributed_pretraining_b200"
+    exe = tmp_path / "host"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", f"-I{ROOT / 'include'}", str(src),
+                    f"-L{lib_dir}", "-lb200hotpath", f"-Wl,-rpath,{lib_dir}", "-o", str(exe)], check=True)
+    assert subprocess.run([str(exe)]).returncode == 0
