@@ -58,15 +58,27 @@ def main():
         if e > cur_end:
             busy += e - max(cur_s, s) if s > cur_end else e - cur_end
             cur_end = e
+    per = defaultdict(lambda: [0, 0.0])
+    for s_, e_, name in ev:
+        short = name.replace("(anonymous namespace)::", "").replace("void ", "").replace("b200::", "")
+        q = per[short.split("(")[0][:70]]
+        q[0] += 1
+        q[1] += e_ - s_
     wall = t1 - t0
     top = sorted(gaps.items(), key=lambda kv: -kv[1][1])[:25]
     out = {"tag": tag, "steps": steps, "wall_us_per_step": wall / steps, "busy_us_per_step": busy / steps,
            "idle_us_per_step": (wall - busy) / steps, "kernels_per_step": len(ev) / steps,
+           "kernel_time_in_situ_top": [{"kernel": kname, "count_per_step": v[0] / steps, "us_per_launch": v[1] / v[0],
+                                        "us_per_step": v[1] / steps}
+                                       for kname, v in sorted(per.items(), key=lambda kv: -kv[1][1])[:40]],
            "idle_before_kernel_top": [{"kernel": kname, "count_per_step": v[0] / steps, "idle_us_per_step": v[1] / steps}
                                       for kname, v in top]}
     (ROOT / "gpurun_out").mkdir(exist_ok=True)
     (ROOT / "gpurun_out" / f"gpu_gaps_{tag}.json").write_text(json.dumps(out, indent=1))
-    print({k2: (round(v, 1) if isinstance(v, float) else v) for k2, v in out.items() if k2 != "idle_before_kernel_top"})
+    print({k2: (round(v, 1) if isinstance(v, float) else v) for k2, v in out.items()
+           if k2 not in ("idle_before_kernel_top", "kernel_time_in_situ_top")})
+    for r in out["kernel_time_in_situ_top"][:30]:
+        print(f"    {r['us_per_step']:8.1f} us/step  {r['count_per_step']:5.1f} x {r['us_per_launch']:7.1f} us  {r['kernel']}")
     for r in out["idle_before_kernel_top"][:12]:
         print("   ", round(r["idle_us_per_step"], 1), "us idle before", r["count_per_step"], "x", r["kernel"])
 
