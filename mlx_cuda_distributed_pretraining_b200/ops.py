@@ -930,7 +930,7 @@ def mlp(x: torch.Tensor, wg: torch.Tensor, wu: torch.Tensor, wd: torch.Tensor) -
 
 
 # B200_MLP_FUSED=0 restores the library GEMMs + elementwise GLU kernels (A/B switch for measurements; the first
-# version of the fused epilogues, with row-per-lane 16-byte stores, LOST to that pair -- see DESIGN.md section 4.6)
+# version of the fused epilogues, with row-per-lane 16-byte stores, LOST to that pair -- see DESIGN.md sections 4.7 and 9)
 _MLP_FUSED = os.environ.get("B200_MLP_FUSED", "1") != "0"
 
 

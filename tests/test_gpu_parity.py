@@ -1,6 +1,6 @@
 """-m gpu: the CUDA path, called through the C ABI, against the oracle and the golden vectors.
 
-Tolerances (relative Frobenius error unless noted; see DESIGN.md section "Parity"):
+Tolerances (relative Frobenius error unless noted; see DESIGN.md section 5 "Oracle and parity"):
   fp32 elementwise kernels            1e-6      (same formula, fp32)
   bf16-output kernels                 4e-3      (one bf16 rounding of the result, 2^-8 relative)
   GEMM, fp32 out, bf16 operands       2e-6      (exact products, fp32 accumulation order)
