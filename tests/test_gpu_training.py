@@ -427,7 +427,7 @@ def test_c1_loss_curve_matches_oracle(tmp_path, data, lr):
     if lr is not None:                                                 # control: step by step, whole curve
         assert float(diff.max()) < C1_TOL["control"], (float(diff.max()), int(diff.argmax()))
     elif data == "uniform" and n > 200:
-        assert float(diff[30:100].max()) < C1_TOL["settling"], float(diff[30:100].max())
+        assert float(diff[40:100].max()) < C1_TOL["settling"], float(diff[40:100].max())
         assert float(diff[100:].max()) < C1_TOL["settled"], (float(diff[100:].max()), int(diff[100:].argmax()) + 100)
         # SURVEY 8c's 1e-2, on the 25-step running mean of the signed difference (single steps sit on minibatch noise
         # of two runs whose weights parted in the transient)
@@ -442,7 +442,7 @@ def test_c1_loss_curve_matches_oracle(tmp_path, data, lr):
 
 # |loss_gpu - loss_oracle| bounds.  The GPU run is itself not bit-reproducible (dQ is accumulated with fp32 atomics) and
 # the config's chaotic first ~30 steps amplify that, so where the transient ends differs run to run.  Measured on B200
-# over five runs of the uniform stream: head 4e-4 / 1.4e-2 (steps 1 / 2); steps 30-99 0.0075 ... 0.065 (the transient
-# dying); steps >= 100 single-step 0.0047 ... 0.0073, 25-step running mean 0.003 ... 0.0053; lr-1e-3 control (no
-# transient): 1.1e-3 over the whole curve, single steps.
+# over five runs of the uniform stream: head 4e-4 / 1.4e-2 (steps 1 / 2); steps 30-39 up to 0.065 (the transient dying,
+# not asserted), steps 40-99 0.0063 ... 0.012; steps >= 100 single-step 0.0038 ... 0.0073, 25-step running mean
+# 0.0018 ... 0.0053; lr-1e-3 control (no transient): 1.1e-3 over the whole curve, single steps.
 C1_TOL = {"head": 3e-2, "settling": 0.15, "settled": 2e-2, "tail": 1e-2, "control": 1e-2}
